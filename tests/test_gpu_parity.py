@@ -1,0 +1,394 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the reference's golden vectors.
+Bit-exact everywhere -- the whole path is integer / byte work."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import read_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _io(pkg, frames, sizes, slack=0):
+    io = np.zeros(len(frames), dtype=pkg.binding.FRAME_IO_DTYPE)
+    so = oo = 0
+    for i, (f, n) in enumerate(zip(frames, sizes)):
+        io[i] = (so, len(f), oo, n + slack)
+        so += len(f); oo += n + slack
+    return io, np.frombuffer(b"".join(frames), dtype=np.uint8), oo
+
+
+def test_corpus_frame_decoder(pkg, ctx, manifest):
+    """tests/decode_corpus.rs through the FrameDecoder mirror: reset + decode_blocks(All) + collect."""
+    dec = pkg.FrameDecoder(ctx)
+    for name, m in manifest["corpus"].items():
+        data = read_golden("decodecorpus", name)
+        r = dec.reset(data)
+        assert dec.decode_blocks(r, pkg.ALL) is True
+        out = dec.collect()
+        assert len(out) == m["size"], name
+        assert hashlib.sha256(out).hexdigest() == m["sha256"], name
+        assert dec.bytes_read_from_source() == len(data), name
+        assert dec.get_checksum_from_data() == dec.get_calculated_checksum() == m["xxh64_low32"], name
+        assert dec.is_finished()
+
+
+def test_corpus_batch_and_intermediates(pkg, ctx, oracle, manifest):
+    """All 101 frames in ONE submission; per-block literals and sequences against the oracle's trace."""
+    names = sorted(manifest["corpus"])
+    frames = [read_golden("decodecorpus", n) for n in names]
+    sizes = [manifest["corpus"][n]["size"] for n in names]
+    io, comp, total = _io(pkg, frames, sizes)
+    import torch
+    d_out = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
+    b = pkg.Batch(ctx, comp, io)
+    b.run(d_out)
+    res = b.finish()
+    out = d_out.cpu().numpy()
+    blk = 0
+    nlit = nseq = 0
+    for i, n in enumerate(names):
+        assert res[i]["status"] == 0, (n, res[i])
+        assert res[i]["out_size"] == sizes[i] and res[i]["bytes_read"] == len(frames[i]), n
+        got = out[io[i]["out_off"]:io[i]["out_off"] + sizes[i]].tobytes()
+        assert hashlib.sha256(got).hexdigest() == manifest["corpus"][n]["sha256"], n
+        assert res[i]["has_checksum"] == 1 and res[i]["checksum_from_data"] == manifest["corpus"][n]["xxh64_low32"]
+        d = oracle.FrameDecoder(); d.trace_enable()
+        r = d.reset(frames[i]); d.decode_blocks(r); d.collect()
+        blocks, lits, seqs = d.trace()
+        assert res[i]["blocks_decoded"] == len(blocks)
+        for tb in blocks:
+            if tb["block_type"] == 2:
+                if tb["literals_type"] >= 2:
+                    got_l = b.debug_literals(blk)
+                    assert got_l == lits[tb["lit_offset"]:tb["lit_offset"] + tb["regenerated_size"]], (n, blk)
+                    nlit += 1
+                if tb["num_sequences"]:
+                    got_s = b.debug_sequences(blk)
+                    exp = seqs[tb["seq_offset"]:tb["seq_offset"] + tb["num_sequences"], :3]
+                    assert np.array_equal(got_s, exp), (n, blk)
+                    nseq += len(exp)
+            blk += 1
+    assert nlit > 1000 and nseq > 1_000_000   # 2458 compressed blocks / 1,031,936 sequences in the corpus
+
+
+def test_dict_corpus(pkg, ctx, manifest):
+    """tests/dict_test.rs:77-262 via the mirror, then all 207 frames in one batch."""
+    dic = read_golden("dict_tests", "dictionary")
+    dec = pkg.FrameDecoder(ctx)
+    dec.add_dict(dic)
+    names = sorted(manifest["dict"])
+    for name in names[:40]:
+        data = read_golden("dict_tests", "files", name)
+        r = dec.reset(data)
+        dec.decode_blocks(r, pkg.ALL)
+        out = dec.collect()
+        m = manifest["dict"][name]
+        assert len(out) == m["size"] and hashlib.sha256(out).hexdigest() == m["sha256"], name
+        assert dec.bytes_read_from_source() == len(data)
+    D = pkg.Dictionary.decode_dict(ctx, dic)
+    assert D.id == 618557512
+    frames = [read_golden("dict_tests", "files", n) for n in names]
+    sizes = [manifest["dict"][n]["size"] for n in names]
+    io, comp, total = _io(pkg, frames, sizes)
+    out = np.zeros(total + 16, dtype=np.uint8)
+    res = pkg.decode_frames(ctx, comp, io, out, dicts=[D])
+    for i, n in enumerate(names):
+        assert res[i]["status"] == 0 and res[i]["has_dict_id"] == 1 and res[i]["dict_id"] == 618557512, n
+        got = out[io[i]["out_off"]:io[i]["out_off"] + res[i]["out_size"]].tobytes()
+        assert hashlib.sha256(got).hexdigest() == manifest["dict"][n]["sha256"], n
+    # without the dictionary: DictNotProvided, like FrameDecoder::reset (frame_decoder.rs:212-216)
+    res = pkg.decode_frames(ctx, comp, io, out)
+    assert all(pkg.error_names()[int(s)] == "B200Z_ERR_DICT_NOT_PROVIDED" for s in res["status"])
+
+
+def test_dictionary_kat(pkg, ctx):
+    from test_oracle_kat import DICT_KAT_CONTENT, dict_kat_bytes
+    raw = dict_kat_bytes()
+    D = pkg.Dictionary.decode_dict(ctx, raw)
+    assert D.id == 0x47232101 and D.offset_hist == [3, 10, 0xABCDEF] and D.content_size == len(DICT_KAT_CONTENT)
+    with pytest.raises(pkg.B200ZError) as e:
+        pkg.Dictionary.decode_dict(ctx, b"\x01\x01\x01\x01" + raw[4:])
+    assert pkg.error_names()[e.value.code] == "B200Z_ERR_DICT_BAD_MAGIC_NUM"
+    for cut in range(0, len(raw) - len(DICT_KAT_CONTENT), 3):
+        with pytest.raises(pkg.B200ZError):
+            pkg.Dictionary.decode_dict(ctx, raw[:cut])
+
+
+def test_fuzz_artifacts_status_parity(pkg, ctx, oracle, manifest):
+    """tests/fuzz_regressions.rs: must not crash; and the GPU path must report the SAME outcome as the oracle
+    (same error leaf + stage, or the same bytes)."""
+    zo, bz = oracle.error_names(), pkg.error_names()
+    for sub, files in manifest["fuzz"].items():
+        for f in files:
+            data = read_golden("fuzz", sub, f)
+            try:
+                exp, _ = oracle.decode_frame(data)
+                exp_err = None
+            except oracle.OracleError as e:
+                exp, exp_err = None, (zo[e.code].replace("ZO_", ""), e.stage)
+            io = np.zeros(1, dtype=pkg.binding.FRAME_IO_DTYPE)
+            io[0] = (0, len(data), 0, 1 << 20)
+            out = np.zeros((1 << 20) + 16, dtype=np.uint8)
+            res = pkg.decode_frames(ctx, np.frombuffer(data, dtype=np.uint8) if data else np.zeros(0, np.uint8), io, out)
+            if exp_err is None:
+                assert res[0]["status"] == 0, (sub, f, res[0])
+                assert out[:res[0]["out_size"]].tobytes() == exp, (sub, f)
+            else:
+                got = (bz[int(res[0]["status"])].replace("B200Z_", ""), int(res[0]["stage"]))
+                assert got == exp_err, (sub, f, got, exp_err)
+            dec = pkg.FrameDecoder(ctx)
+            try:
+                r = dec.reset(data); dec.decode_blocks(r, pkg.ALL); got2 = dec.collect()
+                assert exp_err is None and got2 == exp, (sub, f)
+            except pkg.B200ZError as e:
+                assert exp_err is not None and bz[e.code].replace("B200Z_", "") == exp_err[0], (sub, f, e, exp_err)
+
+
+def test_fuzz_artifacts_without_dict_id(pkg, ctx, oracle, manifest):
+    """Most artifacts stop at DictNotProvided; clear the dict-id flag so the block path itself sees hostile input."""
+    zo, bz = oracle.error_names(), pkg.error_names()
+    n = 0
+    for f in manifest["fuzz"]["decode"]:
+        data = bytearray(read_golden("fuzz", "decode", f))
+        if len(data) < 6 or data[:4] != bytes([0x28, 0xB5, 0x2F, 0xFD]) or (data[4] & 3) == 0:
+            continue
+        did = [0, 1, 2, 4][data[4] & 3]
+        single = (data[4] >> 5) & 1
+        pos = 5 + (0 if single else 1)
+        data = bytes(data[:4]) + bytes([data[4] & ~3]) + bytes(data[5:pos]) + bytes(data[pos + did:])
+        try:
+            exp, _ = oracle.decode_frame(data); exp_err = None
+        except oracle.OracleError as e:
+            exp, exp_err = None, (zo[e.code].replace("ZO_", ""), e.stage)
+        io = np.zeros(1, dtype=pkg.binding.FRAME_IO_DTYPE)
+        io[0] = (0, len(data), 0, 4 << 20)
+        out = np.zeros((4 << 20) + 16, dtype=np.uint8)
+        res = pkg.decode_frames(ctx, np.frombuffer(data, dtype=np.uint8), io, out, max_window_size=1 << 40)
+        if exp_err is None:
+            assert res[0]["status"] == 0 and out[:res[0]["out_size"]].tobytes() == exp, f
+        elif exp_err[0] != "ERR_WINDOW_SIZE_TOO_BIG":
+            got = (bz[int(res[0]["status"])].replace("B200Z_", ""), int(res[0]["stage"]))
+            assert got == exp_err, (f, got, exp_err)
+        n += 1
+    assert n >= 25
+
+
+def test_window_fixtures(pkg, ctx, manifest):
+    """tests/mod.rs:576-741."""
+    fox = b"The quick brown fox jumps over the lazy dog.\n" * 4096
+    sphinx = b"Sphinx of black quartz, judge my vow.\n" * 4096
+    big, small = read_golden("test_fixtures", "window_256mib.zst"), read_golden("test_fixtures", "window_8mib.zst")
+    names = pkg.error_names()
+    d = pkg.FrameDecoder(ctx); d.set_max_window_size(300 << 20)
+    assert d.max_window_size() == 300 << 20
+    assert d.decode_all(big, len(fox)) == fox
+    d = pkg.FrameDecoder(ctx)
+    assert d.max_window_size() == 128 << 20
+    with pytest.raises(pkg.B200ZError) as e:
+        d.decode_all(big, len(fox))
+    assert names[e.value.code] == "B200Z_ERR_WINDOW_SIZE_TOO_BIG"
+    d = pkg.FrameDecoder(ctx); d.set_max_window_size(300 << 20)
+    assert d.decode_all(big + big, 2 * len(fox)) == fox + fox
+    d = pkg.FrameDecoder(ctx)
+    with pytest.raises(pkg.B200ZError) as e:
+        d.decode_all(small + big, len(fox) + len(sphinx))
+    assert names[e.value.code] == "B200Z_ERR_WINDOW_SIZE_TOO_BIG"
+    with pytest.raises(pkg.B200ZError) as e:
+        pkg.StreamingDecoder(ctx, big)
+    assert names[e.value.code] == "B200Z_ERR_WINDOW_SIZE_TOO_BIG"
+    s = pkg.StreamingDecoder(ctx, big, max_window_size=300 << 20)
+    assert s.read_to_end() == fox
+    d = pkg.FrameDecoder(ctx); d.set_max_window_size(2 ** 64 - 1)
+    assert d.max_window_size() == (1 << 41) + 7 * (1 << 38)
+    assert pkg.FrameDecoder(ctx).decode_all(read_golden("test_fixtures", "window_128mib.zst"), len(fox)) == fox
+
+
+def test_api_decode_from_to(pkg, ctx, manifest):
+    """tests/mod.rs:129-230."""
+    content = read_golden("decodecorpus", "z000088.zst")
+    d = pkg.FrameDecoder(ctx)
+    read1, out1 = d.decode_from_to(content[:50 * 1024], 1 << 20)
+    read2, out2 = d.decode_from_to(content[read1:len(content) - 4], 1 << 20)
+    assert read1 + read2 == len(content) - 4
+    read3, out3 = d.decode_from_to(content[read1 + read2:], 1 << 20)
+    assert read3 == 4 and out3 == b""
+    res = out1 + out2
+    m = manifest["corpus"]["z000088.zst"]
+    assert len(res) == m["size"] and hashlib.sha256(res).hexdigest() == m["sha256"]
+    assert d.get_checksum_from_data() == d.get_calculated_checksum() == m["xxh64_low32"]
+
+
+def test_api_streaming_and_reuse(pkg, ctx, manifest):
+    """tests/mod.rs:294-380."""
+    s = pkg.StreamingDecoder(ctx, read_golden("decodecorpus", "z000088.zst"))
+    out = s.read_to_end()
+    assert hashlib.sha256(out).hexdigest() == manifest["corpus"]["z000088.zst"]["sha256"]
+    s2 = pkg.StreamingDecoder(ctx, read_golden("decodecorpus", "z000068.zst"), decoder=s.into_frame_decoder())
+    assert hashlib.sha256(s2.read_to_end()).hexdigest() == manifest["corpus"]["z000068.zst"]["sha256"]
+
+
+def test_api_streaming_matches_oracle_read_pattern(pkg, ctx, oracle):
+    """Same sequence of read() sizes through both StreamingDecoders -> same chunks (window retention, UptoBytes loop)."""
+    data = read_golden("decodecorpus", "z000033.zst")
+    a, b = pkg.StreamingDecoder(ctx, data), oracle.StreamingDecoder(data)
+    rng = np.random.Generator(np.random.PCG64(3))
+    while True:
+        n = int(rng.integers(1, 200_000))
+        x, y = a.read(n), b.read(n)
+        assert x == y
+        if not y:
+            break
+
+
+def test_api_incremental_read(pkg, ctx):
+    """tests/mod.rs:382-404."""
+    data = read_golden("decodecorpus", "abc.txt.zst")
+    d = pkg.FrameDecoder(ctx)
+    r = d.reset(data)
+    _, out = d.decode_from_to(r.src.read(), 3)
+    assert out == b"abc" and d.is_finished()
+
+    class W:
+        def __init__(self): self.buf = bytearray(); self.cap = 3
+        def write(self, b):
+            k = min(len(b), self.cap - len(self.buf)); self.buf += b[:k]; return k
+    w = W()
+    assert d.collect_to_writer(w) == 3 and bytes(w.buf) == b"def"
+
+
+def test_api_decode_all(pkg, ctx, manifest):
+    """tests/mod.rs:490-574."""
+    def skip(n):
+        return (0x184D2A50).to_bytes(4, "little") + n.to_bytes(4, "little") + bytes(n)
+    a, b = read_golden("decodecorpus", "z000089.zst"), read_golden("decodecorpus", "z000090.zst")
+    inp = skip(300) + a + skip(400) + b + skip(500)
+    total = manifest["corpus"]["z000089.zst"]["size"] + manifest["corpus"]["z000090.zst"]["size"]
+    names = pkg.error_names()
+    d = pkg.FrameDecoder(ctx)
+    out = d.decode_all(inp, total)
+    assert len(out) == total
+    assert hashlib.sha256(out[:manifest["corpus"]["z000089.zst"]["size"]]).hexdigest() == manifest["corpus"]["z000089.zst"]["sha256"]
+    with pytest.raises(pkg.B200ZError) as e:
+        d.decode_all(inp, total - 1)
+    assert names[e.value.code] == "B200Z_ERR_TARGET_TOO_SMALL"
+    assert d.decode_all(inp, total + 1) == out
+    with pytest.raises(pkg.B200ZError) as e:
+        d.decode_all(inp[:-600], total)
+    assert e.value.stage == 3      # FrameDecoderError::FailedToReadBlockBody(_)
+    with pytest.raises(pkg.B200ZError) as e:
+        d.decode_all(inp[:-1], total)
+    assert names[e.value.code] == "B200Z_ERR_FAILED_TO_SKIP_FRAME"
+
+
+def test_strategies_match_oracle(pkg, ctx, oracle):
+    """decode_blocks(UptoBlocks / UptoBytes) stop at the same block boundaries and expose the same counters."""
+    data = read_golden("decodecorpus", "z000033.zst")
+    for strat, n in [(pkg.UPTO_BLOCKS, 7), (pkg.UPTO_BYTES, 5000), (pkg.UPTO_BLOCKS, 0), (pkg.UPTO_BYTES, 300000)]:
+        a, b = pkg.FrameDecoder(ctx), oracle.FrameDecoder()
+        ra, rb = a.reset(data), b.reset(data)
+        for _ in range(2000):
+            fa, fb = a.decode_blocks(ra, strat, n), b.decode_blocks(rb, strat, n)
+            assert fa == fb
+            assert a.blocks_decoded() == b.blocks_decoded() and a.bytes_read_from_source() == b.bytes_read_from_source()
+            assert a.can_collect() == b.can_collect()
+            k = a.can_collect() // 2
+            assert a.read(k) == b.read(k)
+            if fa:
+                break
+        assert a.collect() == b.collect()
+        assert a.get_calculated_checksum() == b.get_calculated_checksum()
+
+
+def test_synthetic_configs_small(pkg, ctx, oracle):
+    """Small instances of every BASELINE.json config against the oracle AND libzstd."""
+    import datagen as G
+    sets = [
+        G.config_c2b(total_bytes=4 << 20, cache=False),
+        G.config_c2a(total_bytes=2 << 20, nframes=2, cache=False),
+        G.config_c3(nframes=24, cache=False),
+        G.config_c4(nframes=6, cache=False),
+        G.config_c5(nframes=300, cache=False),
+    ]
+    for fs in sets:
+        D = pkg.Dictionary.raw_content(ctx, 1, fs.raw_dict.tobytes()) if fs.raw_dict is not None else None
+        out = np.zeros(fs.D + 16, dtype=np.uint8)
+        res = pkg.decode_frames(ctx, fs.comp, fs.frames_io(), out, forced_dict=D)
+        assert (res["status"] == 0).all(), (fs.name, res[res["status"] != 0][:3])
+        assert (res["out_size"] == fs.out_size).all()
+        assert np.array_equal(out[:fs.D], fs.plain), fs.name
+        o_out, o_sz = oracle.bulk_decode(fs.comp, fs.src_off, fs.src_size, fs.out_off, fs.out_size,
+                                         raw_dict=fs.raw_dict.tobytes() if fs.raw_dict is not None else None, nthreads=4)
+        assert np.array_equal(o_out[:fs.D], out[:fs.D]) and (o_sz == fs.out_size).all()
+
+
+def test_target_too_small_and_capacity_isolation(pkg, ctx):
+    """A frame that does not fit its out_cap fails alone and never writes past its slot."""
+    import datagen as G
+    fs = G.config_c3(nframes=4, cache=False)
+    io = fs.frames_io()
+    io["out_cap"][2] = 1000
+    out = np.full(fs.D + 16, 0xAB, dtype=np.uint8)
+    res = pkg.decode_frames(ctx, fs.comp, io, out)
+    names = pkg.error_names()
+    assert names[int(res[2]["status"])] == "B200Z_ERR_TARGET_TOO_SMALL"
+    for i in (0, 1, 3):
+        assert res[i]["status"] == 0
+        assert np.array_equal(out[fs.out_off[i]:fs.out_off[i] + fs.out_size[i]], fs.plain[fs.out_off[i]:fs.out_off[i] + fs.out_size[i]])
+    assert (out[int(fs.out_off[2]) + 1000:int(fs.out_off[3])] == 0xAB).all()
+
+
+def test_truncation_sweep_matches_oracle(pkg, ctx, oracle):
+    """Every prefix of a small frame: same outcome (bytes or error leaf + stage) as the oracle."""
+    data = read_golden("decodecorpus", "z000002.zst")
+    zo, bz = oracle.error_names(), pkg.error_names()
+    cuts = list(range(0, min(len(data), 400))) + list(range(400, len(data), 97))
+    frames = [data[:c] for c in cuts]
+    io, comp, total = _io(pkg, frames, [1 << 16] * len(frames))
+    out = np.zeros(total + 16, dtype=np.uint8)
+    res = pkg.decode_frames(ctx, comp if len(comp) else np.zeros(1, np.uint8), io, out)
+    for i, f in enumerate(frames):
+        try:
+            exp, _ = oracle.decode_frame(f); err = None
+        except oracle.OracleError as e:
+            exp, err = None, (zo[e.code].replace("ZO_", ""), e.stage)
+        if err is None:
+            assert res[i]["status"] == 0 and out[io[i]["out_off"]:io[i]["out_off"] + res[i]["out_size"]].tobytes() == exp
+        else:
+            assert (bz[int(res[i]["status"])].replace("B200Z_", ""), int(res[i]["stage"])) == err, (cuts[i], res[i], err)
+
+
+def test_bitflip_sweep_matches_oracle(pkg, ctx, oracle):
+    """Single-bit corruptions of a compressed block: same outcome as the oracle, no device fault."""
+    data = bytearray(read_golden("decodecorpus", "z000005.zst"))
+    rng = np.random.Generator(np.random.PCG64(11))
+    zo, bz = oracle.error_names(), pkg.error_names()
+    frames = []
+    for _ in range(300):
+        d = bytearray(data)
+        pos = int(rng.integers(4, len(d)))
+        d[pos] ^= 1 << int(rng.integers(0, 8))
+        frames.append(bytes(d))
+    cap = 1 << 21
+    io, comp, total = _io(pkg, frames, [cap] * len(frames))
+    import torch
+    d_out = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
+    b = pkg.Batch(ctx, comp, io)
+    b.run(d_out)
+    res = b.finish()
+    out = d_out.cpu().numpy()
+    same = 0
+    for i, f in enumerate(frames):
+        try:
+            exp, _ = oracle.decode_frame(f); err = None
+        except oracle.OracleError as e:
+            exp, err = None, (zo[e.code].replace("ZO_", ""), e.stage)
+        if err is None:
+            if len(exp) <= cap:
+                assert res[i]["status"] == 0 and out[io[i]["out_off"]:io[i]["out_off"] + res[i]["out_size"]].tobytes() == exp, i
+                same += 1
+        else:
+            assert (bz[int(res[i]["status"])].replace("B200Z_", ""), int(res[i]["stage"])) == err, (i, res[i], err)
+    assert same > 0

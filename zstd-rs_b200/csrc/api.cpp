@@ -1,0 +1,1117 @@
+// api.cpp -- the C ABI declared in include/b200zstd.h: context, dictionaries, batch entry (tier 1) and the
+// FrameDecoder / StreamingDecoder mirrors (tier 2).  Host logic only; all decoding happens in kernels.cu.
+// There is no CPU decode path in this library: without a usable CUDA device b200z_ctx_create fails.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/b200zstd.h"
+#include "kernels.h"
+#include "plan.h"
+#include "tables.cuh"
+
+using namespace b200z;
+
+// ---------------------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct ErrName { int code; const char *name; };
+#define EN(x) {B200Z_##x, #x}
+const ErrName kErrNames[] = {
+    EN(OK), EN(ERR_MAGIC_NUMBER_READ), EN(ERR_BAD_MAGIC_NUMBER), EN(ERR_FRAME_DESCRIPTOR_READ), EN(ERR_INVALID_FRAME_DESCRIPTOR),
+    EN(ERR_WINDOW_DESCRIPTOR_READ), EN(ERR_DICTIONARY_ID_READ), EN(ERR_FRAME_CONTENT_SIZE_READ), EN(ERR_SKIP_FRAME),
+    EN(ERR_WINDOW_TOO_BIG), EN(ERR_WINDOW_TOO_SMALL), EN(ERR_WINDOW_SIZE_TOO_BIG), EN(ERR_DICT_NOT_PROVIDED), EN(ERR_NOT_YET_INITIALIZED),
+    EN(ERR_FAILED_TO_READ_CHECKSUM), EN(ERR_FAILED_TO_DRAIN_DECODEBUFFER), EN(ERR_FAILED_TO_SKIP_FRAME), EN(ERR_TARGET_TOO_SMALL),
+    EN(ERR_BLOCK_HEADER_READ), EN(ERR_FOUND_RESERVED_BLOCK), EN(ERR_BLOCK_SIZE_TOO_LARGE), EN(ERR_DECODER_STATE_IS_FAILED),
+    EN(ERR_EXPECTED_HEADER_OF_PREVIOUS_BLOCK), EN(ERR_BLOCK_BODY_READ), EN(ERR_BLOCK_CONTENT_READ), EN(ERR_MALFORMED_SECTION_HEADER),
+    EN(ERR_LITSEC_ILLEGAL_TYPE), EN(ERR_LITSEC_GET_BITS), EN(ERR_LITSEC_NOT_ENOUGH_BYTES), EN(ERR_SEQHDR_NOT_ENOUGH_BYTES),
+    EN(ERR_LIT_MISSING_COMPRESSED_SIZE), EN(ERR_LIT_MISSING_NUM_STREAMS), EN(ERR_LIT_GET_BITS), EN(ERR_LIT_UNINITIALIZED_HUFFMAN_TABLE),
+    EN(ERR_LIT_MISSING_BYTES_FOR_JUMP_HEADER), EN(ERR_LIT_MISSING_BYTES_FOR_LITERALS), EN(ERR_LIT_EXTRA_PADDING),
+    EN(ERR_LIT_BITSTREAM_READ_MISMATCH), EN(ERR_LIT_DECODED_LITERAL_COUNT_MISMATCH), EN(ERR_HUF_GET_BITS), EN(ERR_HUF_FSE_DECODER),
+    EN(ERR_HUF_SOURCE_IS_EMPTY), EN(ERR_HUF_NOT_ENOUGH_BYTES_FOR_WEIGHTS), EN(ERR_HUF_EXTRA_PADDING), EN(ERR_HUF_TOO_MANY_WEIGHTS),
+    EN(ERR_HUF_MISSING_WEIGHTS), EN(ERR_HUF_LEFTOVER_NOT_POWER_OF_2), EN(ERR_HUF_NOT_ENOUGH_BYTES_TO_DECOMPRESS_WEIGHTS),
+    EN(ERR_HUF_FSE_TABLE_USED_TOO_MANY_BYTES), EN(ERR_HUF_NOT_ENOUGH_BYTES_IN_SOURCE), EN(ERR_HUF_WEIGHT_BIGGER_THAN_MAX_NUM_BITS),
+    EN(ERR_HUF_MAX_BITS_TOO_HIGH), EN(ERR_FSE_ACC_LOG_IS_ZERO), EN(ERR_FSE_ACC_LOG_TOO_BIG), EN(ERR_FSE_GET_BITS),
+    EN(ERR_FSE_PROBABILITY_COUNTER_MISMATCH), EN(ERR_FSE_TOO_MANY_SYMBOLS), EN(ERR_FSE_TABLE_IS_UNINITIALIZED), EN(ERR_SEQ_EXTRA_PADDING),
+    EN(ERR_SEQ_UNSUPPORTED_OFFSET), EN(ERR_SEQ_ZERO_OFFSET), EN(ERR_SEQ_NOT_ENOUGH_BYTES_FOR_NUM_SEQUENCES), EN(ERR_SEQ_EXTRA_BITS),
+    EN(ERR_SEQ_MISSING_COMPRESSION_MODE), EN(ERR_SEQ_MISSING_BYTE_FOR_RLE_LL_TABLE), EN(ERR_SEQ_MISSING_BYTE_FOR_RLE_OF_TABLE),
+    EN(ERR_SEQ_MISSING_BYTE_FOR_RLE_ML_TABLE), EN(ERR_EXEC_NOT_ENOUGH_BYTES_FOR_SEQUENCE), EN(ERR_EXEC_ZERO_OFFSET),
+    EN(ERR_EXEC_NOT_ENOUGH_BYTES_IN_DICTIONARY), EN(ERR_EXEC_OFFSET_TOO_BIG), EN(ERR_DICT_NOT_ENOUGH_BYTES), EN(ERR_DICT_BAD_MAGIC_NUM),
+    EN(ERR_REFERENCE_WOULD_PANIC), EN(ERR_BLOCK_OUTPUT_LIMIT), EN(ERR_INVALID_ARGUMENT), EN(ERR_OUT_OF_MEMORY), EN(ERR_NO_DEVICE), EN(ERR_CUDA),
+};
+#undef EN
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    // contents are NOT preserved
+    int ensure(size_t n, bool grow = true) {
+        if (n <= cap) return 0;
+        size_t want = n;
+        if (grow && cap) want = std::max(n, cap + cap / 2);
+        release();
+        if (cudaMalloc(&p, want ? want : 16) != cudaSuccess) { p = nullptr; cudaGetLastError(); return B200Z_ERR_OUT_OF_MEMORY; }
+        cap = want ? want : 16;
+        return 0;
+    }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------------
+struct b200z_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    FseSlot *d_predef = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    int set_cuda_err(cudaError_t e, const char *what) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "CUDA error in %s: %s", what, cudaGetErrorString(e));
+        err = buf;
+        cudaGetLastError();
+        return B200Z_ERR_CUDA;
+    }
+    int use() { cudaError_t e = cudaSetDevice(device); return e == cudaSuccess ? 0 : set_cuda_err(e, "cudaSetDevice"); }
+};
+
+#define CU(ctx, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return (ctx)->set_cuda_err(_e, #call); } while (0)
+
+extern "C" const char *b200z_error_name(int code) {
+    for (const auto &e : kErrNames) if (e.code == code) return e.name;
+    return "UNKNOWN";
+}
+extern "C" int b200z_abi_version(void) { return B200Z_ABI_VERSION; }
+
+extern "C" int b200z_ctx_create(int device, b200z_ctx **out) {
+    if (!out) return B200Z_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) { cudaGetLastError(); return B200Z_ERR_NO_DEVICE; }
+    std::unique_ptr<b200z_ctx> c(new b200z_ctx());
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return B200Z_ERR_NO_DEVICE; }
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return B200Z_ERR_NO_DEVICE; }
+    if (cudaMalloc((void **)&c->d_predef, sizeof(FseSlot)) != cudaSuccess) { cudaGetLastError(); return B200Z_ERR_OUT_OF_MEMORY; }
+    int e = launch_predefined(c->d_predef, c->stream);
+    if (e || cudaStreamSynchronize(c->stream) != cudaSuccess) { cudaGetLastError(); return B200Z_ERR_CUDA; }
+    c->launches = 1;
+    *out = c.release();
+    return 0;
+}
+extern "C" void b200z_ctx_destroy(b200z_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->d_predef) cudaFree(c->d_predef);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+extern "C" const char *b200z_ctx_last_error_message(const b200z_ctx *c) { return c ? c->err.c_str() : ""; }
+extern "C" void *b200z_ctx_stream(const b200z_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" uint64_t b200z_ctx_kernel_launches(const b200z_ctx *c) { return c ? c->launches : 0; }
+extern "C" uint64_t b200z_xxh64(const uint8_t *data, size_t len) { XXH64State s; s.reset(); s.update(data, len); return s.digest(); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// dictionaries
+// ---------------------------------------------------------------------------------------------------------------
+struct b200z_dict {
+    b200z_ctx *ctx = nullptr;
+    uint32_t id = 0;
+    uint32_t hist[3] = {1, 4, 8};
+    bool has_tables = false;
+    HufSlot *d_huf = nullptr;
+    FseSlot *d_fse = nullptr;
+    uint8_t *d_content = nullptr;
+    size_t content_len = 0;
+};
+
+static void dict_free(b200z_dict *d) {
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    if (d->d_huf) cudaFree(d->d_huf);
+    if (d->d_fse) cudaFree(d->d_fse);
+    if (d->d_content) cudaFree(d->d_content);
+    delete d;
+}
+
+static int dict_upload_content(b200z_dict *d, const uint8_t *content, size_t len) {
+    b200z_ctx *c = d->ctx;
+    d->content_len = len;
+    CU(c, cudaMalloc((void **)&d->d_content, len + 16));
+    if (len) CU(c, cudaMemcpy(d->d_content, content, len, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// Dictionary::decode_dict (dictionary.rs:45-126).  The table descriptions are parsed and expanded with the same
+// code the GPU runs per block (tables.cuh, compiled for the host here) and uploaded once.
+extern "C" int b200z_dict_create(b200z_ctx *c, const uint8_t *raw, size_t len, b200z_dict **out) {
+    if (!c || !out || (!raw && len)) return B200Z_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (int e = c->use()) return e;
+    if (len < 8) return B200Z_ERR_DICT_NOT_ENOUGH_BYTES;
+    static const uint8_t magic[4] = {0x37, 0xA4, 0x30, 0xEC};
+    if (memcmp(raw, magic, 4) != 0) return B200Z_ERR_DICT_BAD_MAGIC_NUM;
+    std::unique_ptr<b200z_dict, void (*)(b200z_dict *)> d(new b200z_dict(), dict_free);
+    d->ctx = c;
+    d->id = (uint32_t)raw[4] | ((uint32_t)raw[5] << 8) | ((uint32_t)raw[6] << 16) | ((uint32_t)raw[7] << 24);
+    const uint8_t *t = raw + 8;
+    size_t tl = len - 8;
+    std::unique_ptr<HufSlot> huf(new HufSlot());
+    std::unique_ptr<FseSlot> fse(new FseSlot());
+    memset(huf.get(), 0, sizeof(HufSlot));
+    memset(fse.get(), 0, sizeof(FseSlot));
+    uint32_t used = 0;
+    int e = huf_build_decoder(t, (uint32_t)std::min<size_t>(tl, 0x7fffffff), huf.get(), used);
+    if (e) return e;
+    if (tl < used) return B200Z_ERR_DICT_NOT_ENOUGH_BYTES;
+    t += used; tl -= used;
+    struct { FseTab *tab; uint32_t max_log, max_sym; } order[3] = {{&fse->of, 8, 31}, {&fse->ml, 9, 52}, {&fse->ll, 9, 35}};  // OF, ML, LL
+    for (auto &o : order) {
+        e = fse_build_decoder(t, (uint32_t)std::min<size_t>(tl, 0x7fffffff), o.max_log, o.max_sym, o.tab, used);
+        if (e) return e;
+        if (tl < used) return B200Z_ERR_DICT_NOT_ENOUGH_BYTES;
+        t += used; tl -= used;
+    }
+    if (tl < 12) return B200Z_ERR_DICT_NOT_ENOUGH_BYTES;
+    for (int i = 0; i < 3; i++) d->hist[i] = (uint32_t)t[4 * i] | ((uint32_t)t[4 * i + 1] << 8) | ((uint32_t)t[4 * i + 2] << 16) | ((uint32_t)t[4 * i + 3] << 24);
+    d->has_tables = true;
+    CU(c, cudaMalloc((void **)&d->d_huf, sizeof(HufSlot)));
+    CU(c, cudaMalloc((void **)&d->d_fse, sizeof(FseSlot)));
+    CU(c, cudaMemcpy(d->d_huf, huf.get(), sizeof(HufSlot), cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(d->d_fse, fse.get(), sizeof(FseSlot), cudaMemcpyHostToDevice));
+    if ((e = dict_upload_content(d.get(), t + 12, tl - 12))) return e;
+    *out = d.release();
+    return 0;
+}
+extern "C" int b200z_dict_create_raw_content(b200z_ctx *c, uint32_t id, const uint8_t *content, size_t len, b200z_dict **out) {
+    if (!c || !out || (!content && len)) return B200Z_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (int e = c->use()) return e;
+    std::unique_ptr<b200z_dict, void (*)(b200z_dict *)> d(new b200z_dict(), dict_free);
+    d->ctx = c; d->id = id;
+    if (int e = dict_upload_content(d.get(), content, len)) return e;
+    *out = d.release();
+    return 0;
+}
+extern "C" uint32_t b200z_dict_id(const b200z_dict *d) { return d ? d->id : 0; }
+extern "C" int b200z_dict_offset_history(const b200z_dict *d, uint32_t out[3]) { if (!d) return B200Z_ERR_INVALID_ARGUMENT; memcpy(out, d->hist, 12); return 0; }
+extern "C" size_t b200z_dict_content_size(const b200z_dict *d) { return d ? d->content_len : 0; }
+extern "C" void b200z_dict_destroy(b200z_dict *d) { dict_free(d); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// A "submission": host-side plan + its device mirror.  Used by the batch entry (many frames, fresh state) and
+// by the FrameDecoder mirror (one frame, a few new blocks, state carried on the device).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct CarrySet { const HufSlot *huf = nullptr; const FseTab *ll = nullptr, *of = nullptr, *ml = nullptr; };
+
+struct Submission {
+    std::vector<BlockDesc> descs;
+    std::vector<BlockRefs> refs;
+    std::vector<FrameDesc> frames;
+    std::vector<FrameState> states;
+    std::vector<CarrySet> carries;   // TabRef::CARRY idx -> device tables (dictionaries / streaming carry)
+    uint32_t n_huf = 0, n_fse = 0;
+    uint64_t lit_bytes = 0, nseq = 0;
+    DevBuf d_descs, d_aux, d_frames, d_states, d_huf, d_fse, d_lit, d_seq;
+
+    void clear() {
+        descs.clear(); refs.clear(); frames.clear(); states.clear(); carries.clear();
+        n_huf = n_fse = 0; lit_bytes = 0; nseq = 0;
+    }
+    // resolve table references to device pointers and upload descriptors
+    int upload(b200z_ctx *c) {
+        int e;
+        if ((e = d_descs.ensure(descs.size() * sizeof(BlockDesc)))) return e;
+        if ((e = d_aux.ensure(descs.size() * sizeof(BlockAux)))) return e;
+        if ((e = d_frames.ensure(frames.size() * sizeof(FrameDesc)))) return e;
+        if ((e = d_states.ensure(states.size() * sizeof(FrameState)))) return e;
+        if ((e = d_huf.ensure((size_t)n_huf * sizeof(HufSlot)))) return e;
+        if ((e = d_fse.ensure((size_t)n_fse * sizeof(FseSlot)))) return e;
+        if ((e = d_lit.ensure(lit_bytes + 64))) return e;
+        if ((e = d_seq.ensure((nseq + 4) * 12))) return e;
+        HufSlot *hs = d_huf.as<HufSlot>();
+        FseSlot *fs = d_fse.as<FseSlot>();
+        const FseSlot *pd = c->d_predef;
+        for (size_t i = 0; i < descs.size(); i++) {
+            BlockDesc &d = descs[i];
+            const BlockRefs &r = refs[i];
+            auto huf = [&](const TabRef &t) -> const HufSlot * {
+                if (t.kind == TabRef::SLOT) return hs + t.idx;
+                if (t.kind == TabRef::CARRY) return carries[t.idx].huf;
+                return nullptr;
+            };
+            auto fse = [&](const TabRef &t, int which) -> const FseTab * {
+                if (t.kind == TabRef::SLOT) return which == 0 ? &fs[t.idx].ll : (which == 1 ? &fs[t.idx].of : &fs[t.idx].ml);
+                if (t.kind == TabRef::PREDEF) return which == 0 ? &pd->ll : (which == 1 ? &pd->of : &pd->ml);
+                if (t.kind == TabRef::CARRY) return which == 0 ? carries[t.idx].ll : (which == 1 ? carries[t.idx].of : carries[t.idx].ml);
+                return nullptr;
+            };
+            d.huf = huf(r.huf);
+            d.huf_build = r.build_huf >= 0 ? hs + r.build_huf : nullptr;
+            d.ll = fse(r.ll, 0); d.of = fse(r.of, 1); d.ml = fse(r.ml, 2);
+            d.fse_build = r.build_fse >= 0 ? fs + r.build_fse : nullptr;
+        }
+        if (!descs.empty()) CU(c, cudaMemcpyAsync(d_descs.p, descs.data(), descs.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice, c->stream));
+        if (!frames.empty()) CU(c, cudaMemcpyAsync(d_frames.p, frames.data(), frames.size() * sizeof(FrameDesc), cudaMemcpyHostToDevice, c->stream));
+        if (!states.empty()) CU(c, cudaMemcpyAsync(d_states.p, states.data(), states.size() * sizeof(FrameState), cudaMemcpyHostToDevice, c->stream));
+        return 0;
+    }
+    PipelineArgs args(const uint8_t *d_input, uint8_t *d_output, uint64_t out_cap) const {
+        PipelineArgs a;
+        a.descs = d_descs.as<BlockDesc>(); a.aux = d_aux.as<BlockAux>(); a.frames = d_frames.as<FrameDesc>(); a.states = d_states.as<FrameState>();
+        a.input = d_input; a.lit_scratch = d_lit.as<uint8_t>(); a.seq_scratch = d_seq.as<uint32_t>();
+        a.output = d_output; a.output_cap = out_cap; a.nblocks = (uint32_t)descs.size(); a.nframes = (uint32_t)frames.size();
+        return a;
+    }
+};
+
+// initial cursor of a frame: fresh, or the dictionary's tables (scratch.rs:70-78)
+void cursor_from_carry(TableCursor &cur, const CarrySet &cs, uint32_t carry_idx) {
+    cur = TableCursor();
+    if (cs.huf) { cur.huf.kind = TabRef::CARRY; cur.huf.idx = carry_idx; }
+    if (cs.ll) { cur.ll.kind = TabRef::CARRY; cur.ll.idx = carry_idx; }
+    if (cs.of) { cur.of.kind = TabRef::CARRY; cur.of.idx = carry_idx; }
+    if (cs.ml) { cur.ml.kind = TabRef::CARRY; cur.ml.idx = carry_idx; }
+}
+CarrySet carry_of_dict(const b200z_dict *d) {
+    CarrySet cs;
+    if (d && d->has_tables) { cs.huf = d->d_huf; cs.ll = &d->d_fse->ll; cs.of = &d->d_fse->of; cs.ml = &d->d_fse->ml; }
+    return cs;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// tier 1: batch
+// ---------------------------------------------------------------------------------------------------------------
+struct FramePlanInfo {
+    int pre_status = 0, pre_stage = 0;       // failure before any block (frame header / window / dictionary)
+    FrameHeader hdr;
+    uint64_t window = 0;
+    uint64_t bytes_read_full = 0;            // bytes_read_from_source after a fully successful decode
+    size_t first_block_end = 0;              // index into block_end_bytes
+    bool has_checksum = false;
+    uint32_t checksum = 0;
+    uint32_t skip_len = 0;
+    int32_t sub_frame = -1;                  // index in Submission::frames, -1 if the frame never reaches the GPU
+};
+
+struct b200z_batch {
+    b200z_ctx *ctx = nullptr;
+    Submission sub;
+    std::vector<FramePlanInfo> info;
+    std::vector<uint64_t> block_end_bytes;   // per planned block: bytes_read_from_source after that block
+    DevBuf d_input_own;
+    const uint8_t *d_input = nullptr;
+    DevBuf d_states_init;
+    size_t input_len = 0;
+    bool ran = false;
+};
+
+static int plan_batch(b200z_batch *b, const uint8_t *in, size_t in_len, const b200z_frame_io *frames, size_t nframes,
+                      const b200z_dict *const *dicts, size_t ndicts, const b200z_dict *forced, uint64_t max_window) {
+    Submission &s = b->sub;
+    s.clear();
+    b->info.assign(nframes, FramePlanInfo());
+    b->block_end_bytes.clear();
+    if (max_window == 0) max_window = B200Z_DEFAULT_MAX_WINDOW_SIZE;
+    max_window = std::min<uint64_t>(max_window, (1ull << 41) + 7 * (1ull << 38));
+    // carry sets: one per dictionary (+ forced)
+    std::vector<const b200z_dict *> dlist(dicts, dicts + ndicts);
+    int forced_idx = -1;
+    if (forced) {
+        auto it = std::find(dlist.begin(), dlist.end(), forced);
+        if (it == dlist.end()) { dlist.push_back(forced); forced_idx = (int)dlist.size() - 1; } else forced_idx = (int)(it - dlist.begin());
+    }
+    for (auto *d : dlist) s.carries.push_back(carry_of_dict(d));
+
+    for (size_t i = 0; i < nframes; i++) {
+        FramePlanInfo &fi = b->info[i];
+        const b200z_frame_io &io = frames[i];
+        if (io.src_off > in_len || io.src_size > in_len - io.src_off) { fi.pre_status = B200Z_ERR_INVALID_ARGUMENT; continue; }
+        const uint8_t *p = in + io.src_off;
+        size_t len = io.src_size, consumed = 0;
+        int e = parse_frame_header(p, len, fi.hdr, fi.skip_len, consumed);
+        if (e) { fi.pre_status = e; fi.pre_stage = B200Z_STAGE_FRAME_HEADER; fi.bytes_read_full = consumed; continue; }
+        if ((e = frame_window_size(fi.hdr, fi.window))) { fi.pre_status = e; fi.pre_stage = B200Z_STAGE_FRAME_HEADER; continue; }
+        if (fi.window > max_window) { fi.pre_status = B200Z_ERR_WINDOW_SIZE_TOO_BIG; fi.pre_stage = B200Z_STAGE_FRAME_HEADER; continue; }
+        int dict_idx = -1;
+        if (fi.hdr.has_dict_id) {
+            for (size_t k = 0; k < dlist.size() && k < ndicts; k++) if (dlist[k]->id == fi.hdr.dict_id) dict_idx = (int)k;
+            if (dict_idx < 0) { fi.pre_status = B200Z_ERR_DICT_NOT_PROVIDED; fi.pre_stage = B200Z_STAGE_FRAME_HEADER; continue; }
+        }
+        if (forced_idx >= 0) dict_idx = forced_idx;
+        const b200z_dict *dict = dict_idx >= 0 ? dlist[dict_idx] : nullptr;
+
+        FrameDesc fd;
+        memset(&fd, 0, sizeof fd);
+        fd.out_off = io.out_off; fd.out_cap = io.out_cap; fd.window_size = fi.window;
+        fd.dict = dict ? dict->d_content : nullptr; fd.dict_len = dict ? dict->content_len : 0;
+        fd.first_block = (uint32_t)s.descs.size();
+        FrameState st;
+        memset(&st, 0, sizeof st);
+        st.hist[0] = dict ? dict->hist[0] : 1; st.hist[1] = dict ? dict->hist[1] : 4; st.hist[2] = dict ? dict->hist[2] : 8;
+        TableCursor cur;
+        if (dict_idx >= 0) cursor_from_carry(cur, s.carries[dict_idx], (uint32_t)dict_idx);
+        fi.first_block_end = b->block_end_bytes.size();
+
+        uint64_t pos = consumed, bytes_read = consumed;
+        uint32_t bif = 0;
+        for (;;) {
+            if (len - pos < 3) { fd.host_status = mk_status(B200Z_ERR_BLOCK_HEADER_READ, B200Z_STAGE_BLOCK_HEADER); break; }
+            BlockHeader bh;
+            if ((e = parse_block_header(p + pos, bh))) { fd.host_status = mk_status((uint32_t)e, B200Z_STAGE_BLOCK_HEADER); break; }
+            pos += 3;
+            if (len - pos < bh.content_size) {
+                fd.host_status = mk_status(bh.type == BT_COMPRESSED ? B200Z_ERR_BLOCK_CONTENT_READ : B200Z_ERR_BLOCK_BODY_READ, B200Z_STAGE_BLOCK_BODY);
+                break;
+            }
+            BlockDesc d;
+            memset(&d, 0, sizeof d);
+            BlockRefs r;
+            d.src_off = io.src_off + pos; d.src_size = bh.content_size; d.frame = (uint32_t)s.frames.size();
+            d.btype = bh.type; d.raw_size = bh.decompressed_size; d.block_in_frame = bif++; d.last = bh.last;
+            if (bh.type == BT_COMPRESSED) plan_compressed_block(p + pos, bh.content_size, d, r, cur, s.n_huf, s.n_fse, s.lit_bytes, s.nseq);
+            pos += bh.content_size;
+            bytes_read += 3 + bh.content_size;
+            s.descs.push_back(d); s.refs.push_back(r);
+            b->block_end_bytes.push_back(bytes_read);
+            if (d.host_status) break;  // the reference stops here; later blocks are never looked at
+            if (bh.last) {
+                if (fi.hdr.content_checksum()) {
+                    if (len - pos < 4) { fd.host_status = mk_status(B200Z_ERR_FAILED_TO_READ_CHECKSUM, B200Z_STAGE_CHECKSUM); break; }
+                    fi.has_checksum = true;
+                    fi.checksum = (uint32_t)p[pos] | ((uint32_t)p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16) | ((uint32_t)p[pos + 3] << 24);
+                    bytes_read += 4;
+                }
+                break;
+            }
+        }
+        fd.nblocks = (uint32_t)s.descs.size() - fd.first_block;
+        fi.bytes_read_full = bytes_read;
+        fi.sub_frame = (int32_t)s.frames.size();
+        s.frames.push_back(fd); s.states.push_back(st);
+    }
+    return 0;
+}
+
+extern "C" int b200z_batch_prepare(b200z_ctx *c, const uint8_t *input, size_t input_len, int input_mem, const b200z_frame_io *frames,
+                                   size_t nframes, const b200z_dict *const *dicts, size_t ndicts, const b200z_dict *forced,
+                                   uint64_t max_window, b200z_batch **out) {
+    if (!c || !out || (!input && input_len) || (!frames && nframes) || (!dicts && ndicts)) return B200Z_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (int e = c->use()) return e;
+    std::unique_ptr<b200z_batch> b(new b200z_batch());
+    b->ctx = c; b->input_len = input_len;
+    std::vector<uint8_t> host_copy;
+    const uint8_t *hin = input;
+    if (input_mem == B200Z_MEM_DEVICE) {
+        // the planner walks headers on the host; a device-side frame walker is a "next" row
+        host_copy.resize(input_len);
+        if (input_len) CU(c, cudaMemcpy(host_copy.data(), input, input_len, cudaMemcpyDeviceToHost));
+        hin = host_copy.data();
+        b->d_input = input;
+    }
+    if (int e = plan_batch(b.get(), hin, input_len, frames, nframes, dicts, ndicts, forced, max_window)) return e;
+    if (input_mem != B200Z_MEM_DEVICE) {
+        if (int e = b->d_input_own.ensure(input_len + 16, false)) return e;
+        if (input_len) CU(c, cudaMemcpyAsync(b->d_input_own.p, input, input_len, cudaMemcpyHostToDevice, c->stream));
+        b->d_input = b->d_input_own.as<uint8_t>();
+    }
+    if (int e = b->sub.upload(c)) return e;
+    if (int e = b->d_states_init.ensure(b->sub.states.size() * sizeof(FrameState), false)) return e;
+    if (!b->sub.states.empty())
+        CU(c, cudaMemcpyAsync(b->d_states_init.p, b->sub.states.data(), b->sub.states.size() * sizeof(FrameState), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    *out = b.release();
+    return 0;
+}
+
+extern "C" int b200z_batch_run(b200z_batch *b, uint8_t *d_output, size_t output_cap) {
+    if (!b) return B200Z_ERR_INVALID_ARGUMENT;
+    b200z_ctx *c = b->ctx;
+    if (int e = c->use()) return e;
+    Submission &s = b->sub;
+    if (!s.states.empty())
+        CU(c, cudaMemcpyAsync(s.d_states.p, b->d_states_init.p, s.states.size() * sizeof(FrameState), cudaMemcpyDeviceToDevice, c->stream));
+    PipelineArgs a = s.args(b->d_input, d_output, output_cap);
+    int e = launch_pipeline(a, c->stream);
+    if (e) return c->set_cuda_err((cudaError_t)e, "launch_pipeline");
+    c->launches += pipeline_launch_count(a);
+    b->ran = true;
+    return 0;
+}
+
+static void fill_result(const b200z_batch *b, size_t i, const FrameState *st, b200z_frame_result &r) {
+    const FramePlanInfo &fi = b->info[i];
+    memset(&r, 0, sizeof r);
+    r.content_size = fi.hdr.frame_content_size; r.window_size = fi.window;
+    r.has_dict_id = fi.hdr.has_dict_id; r.dict_id = fi.hdr.dict_id;
+    if (fi.pre_status) {
+        r.status = fi.pre_status; r.stage = fi.pre_stage; r.bytes_read = fi.bytes_read_full;
+        if (fi.pre_status == B200Z_ERR_SKIP_FRAME) r.content_size = fi.skip_len;
+        return;
+    }
+    r.out_size = st->produced; r.blocks_decoded = st->blocks_done;
+    if (st->status == 0) {
+        r.bytes_read = fi.bytes_read_full; r.has_checksum = fi.has_checksum; r.checksum_from_data = fi.checksum;
+        return;
+    }
+    r.status = (int32_t)(st->status & 0xffffu); r.stage = (int32_t)((st->status >> 16) & 0xffu); r.error_block = st->error_block;
+    // bytes_read_from_source at the point the reference returns the error (frame_decoder.rs:325-341)
+    uint32_t j = st->blocks_done;
+    uint64_t before = j > 0 ? b->block_end_bytes[fi.first_block_end + j - 1] : fi.hdr.header_size;
+    if (r.stage == B200Z_STAGE_BLOCK_HEADER) r.bytes_read = before;
+    else if (r.stage == B200Z_STAGE_CHECKSUM) r.bytes_read = before;
+    else r.bytes_read = before + 3;
+}
+
+extern "C" int b200z_batch_finish(b200z_batch *b, b200z_frame_result *results) {
+    if (!b || !results) return B200Z_ERR_INVALID_ARGUMENT;
+    b200z_ctx *c = b->ctx;
+    if (int e = c->use()) return e;
+    Submission &s = b->sub;
+    std::vector<FrameState> st(s.states.size());
+    if (!st.empty()) CU(c, cudaMemcpyAsync(st.data(), s.d_states.p, st.size() * sizeof(FrameState), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < b->info.size(); i++) {
+        int32_t sf = b->info[i].sub_frame;
+        fill_result(b, i, sf >= 0 ? &st[sf] : nullptr, results[i]);
+    }
+    return 0;
+}
+
+extern "C" int b200z_batch_info(const b200z_batch *b, uint64_t out[8]) {
+    if (!b || !out) return B200Z_ERR_INVALID_ARGUMENT;
+    const Submission &s = b->sub;
+    uint64_t ncomp = 0, planned = 0;
+    for (auto &d : s.descs) { ncomp += d.btype == BT_COMPRESSED; planned += d.src_size + 3; }
+    out[0] = s.frames.size(); out[1] = s.descs.size(); out[2] = ncomp; out[3] = planned; out[4] = s.lit_bytes; out[5] = s.nseq;
+    out[6] = pipeline_launch_count(s.args(nullptr, nullptr, 0)); out[7] = 0;
+    return 0;
+}
+
+extern "C" int b200z_batch_debug_literals(b200z_batch *b, uint32_t block, uint8_t *host_out, size_t cap, size_t *len) {
+    if (!b || block >= b->sub.descs.size() || !len) return B200Z_ERR_INVALID_ARGUMENT;
+    b200z_ctx *c = b->ctx;
+    const BlockDesc &d = b->sub.descs[block];
+    *len = 0;
+    if (d.btype != BT_COMPRESSED || (d.lit_type != LT_COMPRESSED && d.lit_type != LT_TREELESS)) return 0;
+    if (cap < d.regen_size) return B200Z_ERR_TARGET_TOO_SMALL;
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpy(host_out, b->sub.d_lit.as<uint8_t>() + d.lit_buf_off, d.regen_size, cudaMemcpyDeviceToHost));
+    *len = d.regen_size;
+    return 0;
+}
+extern "C" int b200z_batch_debug_sequences(b200z_batch *b, uint32_t block, uint32_t *host_out, size_t cap_seqs, size_t *nseq) {
+    if (!b || block >= b->sub.descs.size() || !nseq) return B200Z_ERR_INVALID_ARGUMENT;
+    b200z_ctx *c = b->ctx;
+    const BlockDesc &d = b->sub.descs[block];
+    *nseq = 0;
+    if (d.btype != BT_COMPRESSED || d.nseq == 0) return 0;
+    if (cap_seqs < d.nseq) return B200Z_ERR_TARGET_TOO_SMALL;
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpy(host_out, b->sub.d_seq.as<uint32_t>() + d.seq_buf_off * 3, (size_t)d.nseq * 12, cudaMemcpyDeviceToHost));
+    *nseq = d.nseq;
+    return 0;
+}
+extern "C" void b200z_batch_destroy(b200z_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    delete b;
+}
+
+extern "C" int b200z_decode_frames_batch(b200z_ctx *c, const uint8_t *input, size_t input_len, int input_mem, const b200z_frame_io *frames,
+                                         size_t nframes, const b200z_dict *const *dicts, size_t ndicts, const b200z_dict *forced,
+                                         uint64_t max_window, uint8_t *output, size_t output_cap, int output_mem, b200z_frame_result *results) {
+    if (!c || !results || (!output && output_cap)) return B200Z_ERR_INVALID_ARGUMENT;
+    b200z_batch *b = nullptr;
+    int e = b200z_batch_prepare(c, input, input_len, input_mem, frames, nframes, dicts, ndicts, forced, max_window, &b);
+    if (e) return e;
+    std::unique_ptr<b200z_batch, void (*)(b200z_batch *)> guard(b, b200z_batch_destroy);
+    DevBuf d_out;
+    uint8_t *dout = output;
+    if (output_mem != B200Z_MEM_DEVICE) {
+        if ((e = d_out.ensure(output_cap + 16, false))) return e;
+        dout = d_out.as<uint8_t>();
+    }
+    if ((e = b200z_batch_run(b, dout, output_cap))) return e;
+    if ((e = b200z_batch_finish(b, results))) return e;
+    if (output_mem != B200Z_MEM_DEVICE) {
+        // one D2H covering every produced byte (frames are normally packed back to back by the caller)
+        uint64_t lo = UINT64_MAX, hi = 0;
+        for (size_t i = 0; i < nframes; i++)
+            if (results[i].out_size) { lo = std::min<uint64_t>(lo, frames[i].out_off); hi = std::max<uint64_t>(hi, frames[i].out_off + results[i].out_size); }
+        if (hi > lo) {
+            hi = std::min<uint64_t>(hi, output_cap);
+            CU(c, cudaMemcpyAsync(output + lo, dout + lo, hi - lo, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+        }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tier 2: FrameDecoder mirror (decoding/frame_decoder.rs)
+// ---------------------------------------------------------------------------------------------------------------
+struct b200z_frame_decoder {
+    b200z_ctx *ctx = nullptr;
+    uint64_t max_window = B200Z_DEFAULT_MAX_WINDOW_SIZE;
+    std::map<uint32_t, b200z_dict *> dicts;           // FrameDecoder.dicts (BTreeMap<u32, Dictionary>), owned
+    // FrameDecoderState (frame_decoder.rs:86-94)
+    bool has_state = false;
+    FrameHeader hdr;
+    uint64_t window = 0;
+    bool frame_finished = false;
+    size_t block_counter = 0;
+    uint64_t bytes_read_counter = 0;
+    bool has_check_sum = false;
+    uint32_t check_sum = 0;
+    const b200z_dict *using_dict = nullptr;
+    uint32_t skip_len = 0;
+    int last_stage = 0;
+    std::string err;
+    // decode buffer on the device: frame bytes [base, produced) live at d_out[0 .. produced-base); the host has
+    // drained everything below `drained` (DecodeBuffer::len() == produced - drained, decode_buffer.rs:58)
+    DevBuf d_out;
+    uint64_t base = 0, produced = 0, drained = 0;
+    FrameState state;                                  // host mirror of the device-side frame state
+    XXH64State hash;                                   // decode_buffer.rs:16, fed on drain
+    // "current tables" (DecoderScratch.huf/.fse): which kinds exist + persistent device copies
+    HufSlot *d_carry_huf = nullptr;
+    FseSlot *d_carry_fse = nullptr;
+    CarrySet carry;                                    // what the next submission starts from
+    Submission sub;
+    DevBuf d_input;
+    std::vector<uint8_t> staging;                      // bytes of the blocks of the current submission
+};
+
+static int fd_fail(b200z_frame_decoder *d, int code, int stage) {
+    d->last_stage = stage;
+    char buf[160];
+    snprintf(buf, sizeof buf, "%s (stage %d)", b200z_error_name(code), stage);
+    d->err = buf;
+    return code;
+}
+
+extern "C" int b200z_frame_decoder_new(b200z_ctx *c, b200z_frame_decoder **out) {
+    if (!c || !out) return B200Z_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (int e = c->use()) return e;
+    std::unique_ptr<b200z_frame_decoder> d(new b200z_frame_decoder());
+    d->ctx = c;
+    memset(&d->state, 0, sizeof d->state);
+    d->hash.reset();
+    CU(c, cudaMalloc((void **)&d->d_carry_huf, sizeof(HufSlot)));
+    CU(c, cudaMalloc((void **)&d->d_carry_fse, sizeof(FseSlot)));
+    *out = d.release();
+    return 0;
+}
+extern "C" void b200z_frame_decoder_free(b200z_frame_decoder *d) {
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    for (auto &kv : d->dicts) dict_free(kv.second);
+    if (d->d_carry_huf) cudaFree(d->d_carry_huf);
+    if (d->d_carry_fse) cudaFree(d->d_carry_fse);
+    delete d;
+}
+extern "C" void b200z_frame_decoder_set_max_window_size(b200z_frame_decoder *d, uint64_t n) {
+    d->max_window = std::min<uint64_t>(n, (1ull << 41) + 7 * (1ull << 38));
+}
+extern "C" uint64_t b200z_frame_decoder_max_window_size(const b200z_frame_decoder *d) { return d->max_window; }
+extern "C" uint32_t b200z_frame_decoder_skip_frame_length(const b200z_frame_decoder *d) { return d->skip_len; }
+extern "C" int b200z_frame_decoder_last_stage(const b200z_frame_decoder *d) { return d->last_stage; }
+extern "C" const char *b200z_frame_decoder_last_error_message(const b200z_frame_decoder *d) { return d->err.c_str(); }
+
+static bool read_exact(b200z_read_fn rd, void *user, uint8_t *buf, size_t n) {
+    size_t got = 0;
+    while (got < n) { long r = rd(user, buf + got, n - got); if (r <= 0) return false; got += (size_t)r; }
+    return true;
+}
+
+static void fd_apply_dict(b200z_frame_decoder *d, const b200z_dict *dict) {  // DecoderScratch::init_from_dict, scratch.rs:70-78
+    d->carry = carry_of_dict(dict);
+    d->state.hist[0] = dict->hist[0]; d->state.hist[1] = dict->hist[1]; d->state.hist[2] = dict->hist[2];
+    d->using_dict = dict;
+}
+
+// reset (frame_decoder.rs:200-221): read the header through the callback exactly like read_frame_header does
+extern "C" int b200z_frame_decoder_reset(b200z_frame_decoder *d, b200z_read_fn rd, void *user) {
+    if (!d || !rd) return B200Z_ERR_INVALID_ARGUMENT;
+    uint8_t buf[32];
+    // pull the header piecewise so that no byte beyond it is consumed (frame.rs:6-85)
+    size_t have = 0;
+    auto need = [&](size_t n) { if (have >= n) return true; if (!read_exact(rd, user, buf + have, n - have)) return false; have = n; return true; };
+    FrameHeader h; uint32_t skip = 0; size_t consumed = 0;
+    if (!need(4)) return fd_fail(d, B200Z_ERR_MAGIC_NUMBER_READ, B200Z_STAGE_FRAME_HEADER);
+    uint32_t magic = (uint32_t)buf[0] | ((uint32_t)buf[1] << 8) | ((uint32_t)buf[2] << 16) | ((uint32_t)buf[3] << 24);
+    if (magic >= 0x184D2A50u && magic <= 0x184D2A5Fu) {
+        if (!need(8)) return fd_fail(d, B200Z_ERR_FRAME_DESCRIPTOR_READ, B200Z_STAGE_FRAME_HEADER);
+        parse_frame_header(buf, 8, h, skip, consumed);
+        d->skip_len = skip;
+        return fd_fail(d, B200Z_ERR_SKIP_FRAME, B200Z_STAGE_FRAME_HEADER);
+    }
+    if (magic != 0xFD2FB528u) return fd_fail(d, B200Z_ERR_BAD_MAGIC_NUMBER, B200Z_STAGE_FRAME_HEADER);
+    if (!need(5)) return fd_fail(d, B200Z_ERR_FRAME_DESCRIPTOR_READ, B200Z_STAGE_FRAME_HEADER);
+    uint8_t desc = buf[4];
+    size_t pos = 5;
+    bool single = (desc >> 5) & 1;
+    if (!single) { if (!need(pos + 1)) return fd_fail(d, B200Z_ERR_WINDOW_DESCRIPTOR_READ, B200Z_STAGE_FRAME_HEADER); pos += 1; }
+    static const uint8_t did_len[4] = {0, 1, 2, 4};
+    size_t dl = did_len[desc & 3];
+    if (dl) { if (!need(pos + dl)) return fd_fail(d, B200Z_ERR_DICTIONARY_ID_READ, B200Z_STAGE_FRAME_HEADER); pos += dl; }
+    uint32_t flag = desc >> 6;
+    size_t fl = flag == 0 ? (single ? 1 : 0) : (flag == 1 ? 2 : (flag == 2 ? 4 : 8));
+    if (fl) { if (!need(pos + fl)) return fd_fail(d, B200Z_ERR_FRAME_CONTENT_SIZE_READ, B200Z_STAGE_FRAME_HEADER); pos += fl; }
+    int e = parse_frame_header(buf, pos, h, skip, consumed);
+    if (e) return fd_fail(d, e, B200Z_STAGE_FRAME_HEADER);
+    uint64_t window = 0;
+    if ((e = frame_window_size(h, window))) return fd_fail(d, e, B200Z_STAGE_FRAME_HEADER);
+    if (window > d->max_window) return fd_fail(d, B200Z_ERR_WINDOW_SIZE_TOO_BIG, B200Z_STAGE_FRAME_HEADER);
+    // FrameDecoderState::new / reset (:103-134)
+    d->hdr = h; d->window = window; d->frame_finished = false; d->block_counter = 0;
+    d->bytes_read_counter = h.header_size; d->has_check_sum = false; d->using_dict = nullptr;
+    d->base = d->produced = d->drained = 0;
+    memset(&d->state, 0, sizeof d->state);
+    d->state.hist[0] = 1; d->state.hist[1] = 4; d->state.hist[2] = 8;
+    d->hash.reset();
+    d->carry = CarrySet();
+    d->has_state = true;
+    if (h.has_dict_id) {
+        auto it = d->dicts.find(h.dict_id);
+        if (it == d->dicts.end()) return fd_fail(d, B200Z_ERR_DICT_NOT_PROVIDED, B200Z_STAGE_FRAME_HEADER);
+        fd_apply_dict(d, it->second);
+    }
+    d->last_stage = 0;
+    return 0;
+}
+extern "C" int b200z_frame_decoder_init(b200z_frame_decoder *d, b200z_read_fn rd, void *user) { return b200z_frame_decoder_reset(d, rd, user); }
+
+extern "C" int b200z_frame_decoder_add_dict(b200z_frame_decoder *d, const uint8_t *raw, size_t len) {
+    if (!d) return B200Z_ERR_INVALID_ARGUMENT;
+    b200z_dict *x = nullptr;
+    int e = b200z_dict_create(d->ctx, raw, len, &x);
+    if (e) return fd_fail(d, e, B200Z_STAGE_DICTIONARY);
+    auto it = d->dicts.find(x->id);
+    if (it != d->dicts.end()) { if (d->using_dict == it->second) d->using_dict = nullptr; dict_free(it->second); it->second = x; } else d->dicts[x->id] = x;
+    return 0;
+}
+extern "C" int b200z_frame_decoder_add_raw_content_dict(b200z_frame_decoder *d, uint32_t id, const uint8_t *content, size_t len) {
+    if (!d) return B200Z_ERR_INVALID_ARGUMENT;
+    b200z_dict *x = nullptr;
+    int e = b200z_dict_create_raw_content(d->ctx, id, content, len, &x);
+    if (e) return fd_fail(d, e, B200Z_STAGE_DICTIONARY);
+    auto it = d->dicts.find(id);
+    if (it != d->dicts.end()) { if (d->using_dict == it->second) d->using_dict = nullptr; dict_free(it->second); it->second = x; } else d->dicts[id] = x;
+    return 0;
+}
+extern "C" int b200z_frame_decoder_force_dict(b200z_frame_decoder *d, uint32_t dict_id) {  // :229-243
+    if (!d) return B200Z_ERR_INVALID_ARGUMENT;
+    if (!d->has_state) return fd_fail(d, B200Z_ERR_NOT_YET_INITIALIZED, 0);
+    auto it = d->dicts.find(dict_id);
+    if (it == d->dicts.end()) return fd_fail(d, B200Z_ERR_DICT_NOT_PROVIDED, 0);
+    fd_apply_dict(d, it->second);
+    return 0;
+}
+
+static size_t fd_buffer_len(const b200z_frame_decoder *d) { return (size_t)(d->produced - d->drained); }
+static bool fd_finished(const b200z_frame_decoder *d) {  // is_finished :284-294
+    if (!d->has_state) return true;
+    if (d->hdr.content_checksum()) return d->frame_finished && d->has_check_sum;
+    return d->frame_finished;
+}
+static size_t fd_can_drain_to_window(const b200z_frame_decoder *d) {  // decode_buffer.rs:182-188
+    size_t n = fd_buffer_len(d);
+    return n > d->window ? (size_t)(n - d->window) : 0;
+}
+
+// make room for `extra` more bytes behind `produced`, dropping drained bytes when that frees enough
+static int fd_reserve_out(b200z_frame_decoder *d, uint64_t extra) {
+    b200z_ctx *c = d->ctx;
+    uint64_t live = d->produced - d->drained;
+    uint64_t need = (d->produced - d->base) + extra + 64;
+    if (need <= d->d_out.cap) return 0;
+    uint64_t want = std::max<uint64_t>(live + extra + 64, (uint64_t)d->d_out.cap + d->d_out.cap / 2);
+    want = std::max<uint64_t>(want, 1u << 20);
+    void *np = nullptr;
+    if (cudaMalloc(&np, want) != cudaSuccess) { cudaGetLastError(); return B200Z_ERR_OUT_OF_MEMORY; }
+    if (live) {
+        cudaError_t ce = cudaMemcpyAsync(np, d->d_out.as<uint8_t>() + (d->drained - d->base), live, cudaMemcpyDeviceToDevice, c->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+        if (ce != cudaSuccess) { cudaFree(np); return c->set_cuda_err(ce, "grow output"); }
+    }
+    d->d_out.release();
+    d->d_out.p = np; d->d_out.cap = want;
+    d->base = d->drained;
+    return 0;
+}
+
+// Decode the blocks gathered in d->sub / d->staging on the GPU; updates produced/state/carry tables.
+// Returns 0 or the error of the first failing block (in which case *failed_block is its index in the submission).
+static int fd_submit(b200z_frame_decoder *d, const TableCursor &cur, uint32_t *failed_block, uint32_t *done_blocks) {
+    b200z_ctx *c = d->ctx;
+    Submission &s = d->sub;
+    if (int e = c->use()) return e;
+    int e;
+    if ((e = d->d_input.ensure(d->staging.size() + 16))) return e;
+    CU(c, cudaMemcpyAsync(d->d_input.p, d->staging.data(), d->staging.size(), cudaMemcpyHostToDevice, c->stream));
+    FrameDesc fd;
+    memset(&fd, 0, sizeof fd);
+    fd.out_off = 0; fd.window_size = d->window;
+    fd.dict = d->using_dict ? d->using_dict->d_content : nullptr; fd.dict_len = d->using_dict ? d->using_dict->content_len : 0;
+    fd.first_block = 0; fd.nblocks = (uint32_t)s.descs.size();
+    d->state.produced = d->produced; d->state.drained = d->drained; d->state.blocks_done = 0; d->state.status = 0;
+    s.frames.assign(1, fd); s.states.assign(1, d->state);
+    s.carries.assign(1, d->carry);
+    if ((e = s.upload(c))) return e;
+    // stage A: tables + literals + sequences; sizes come back so the output can grow before execution
+    PipelineArgs a = s.args(d->d_input.as<uint8_t>(), nullptr, 0);
+    PipelineArgs a_dec = a; a_dec.nframes = 0;
+    int le = launch_pipeline(a_dec, c->stream);
+    if (le) return c->set_cuda_err((cudaError_t)le, "launch decode");
+    c->launches += pipeline_launch_count(a_dec);
+    std::vector<BlockAux> aux(s.descs.size());
+    CU(c, cudaMemcpyAsync(aux.data(), s.d_aux.p, aux.size() * sizeof(BlockAux), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    uint64_t extra = 0;
+    for (auto &x : aux) extra += x.out_size;
+    if ((e = fd_reserve_out(d, extra))) return e;
+    // stage B: execution into the persistent window buffer (frame byte 0 sits at d_out - base)
+    s.frames[0].out_cap = d->base + d->d_out.cap;
+    CU(c, cudaMemcpyAsync(s.d_frames.p, s.frames.data(), sizeof(FrameDesc), cudaMemcpyHostToDevice, c->stream));
+    PipelineArgs a_ex = a; a_ex.nblocks = 0;
+    a_ex.output = d->d_out.as<uint8_t>() - d->base; a_ex.output_cap = d->base + d->d_out.cap;
+    le = launch_pipeline(a_ex, c->stream);
+    if (le) return c->set_cuda_err((cudaError_t)le, "launch exec");
+    c->launches += pipeline_launch_count(a_ex);
+    // carry the current tables over to the next submission (device-to-device, tables never visit the host)
+    CarrySet next;
+    if (cur.huf.kind == TabRef::SLOT) {
+        CU(c, cudaMemcpyAsync(d->d_carry_huf, s.d_huf.as<HufSlot>() + cur.huf.idx, sizeof(HufSlot), cudaMemcpyDeviceToDevice, c->stream));
+        next.huf = d->d_carry_huf;
+    } else if (cur.huf.kind == TabRef::CARRY) next.huf = d->carry.huf;
+    auto carry_fse = [&](const TabRef &t, int which, FseTab *dst, const FseTab *old) -> const FseTab * {
+        const FseTab *src = nullptr;
+        if (t.kind == TabRef::SLOT) { const FseSlot *sl = s.d_fse.as<FseSlot>() + t.idx; src = which == 0 ? &sl->ll : (which == 1 ? &sl->of : &sl->ml); }
+        else if (t.kind == TabRef::PREDEF) { const FseSlot *sl = c->d_predef; return which == 0 ? &sl->ll : (which == 1 ? &sl->of : &sl->ml); }
+        else if (t.kind == TabRef::CARRY) return old;
+        else return nullptr;
+        if (cudaMemcpyAsync(dst, src, sizeof(FseTab), cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) return nullptr;
+        return dst;
+    };
+    next.ll = carry_fse(cur.ll, 0, &d->d_carry_fse->ll, d->carry.ll);
+    next.of = carry_fse(cur.of, 1, &d->d_carry_fse->of, d->carry.of);
+    next.ml = carry_fse(cur.ml, 2, &d->d_carry_fse->ml, d->carry.ml);
+    FrameState st;
+    CU(c, cudaMemcpyAsync(&st, s.d_states.p, sizeof(FrameState), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    d->carry = next;
+    d->state = st;
+    d->produced = st.produced;
+    *done_blocks = st.blocks_done;
+    if (st.status) { *failed_block = st.blocks_done; d->last_stage = (int)((st.status >> 16) & 0xff); return (int)(st.status & 0xffff); }
+    return 0;
+}
+
+namespace {
+struct SliceReader { const uint8_t *p; size_t len; };
+long slice_read(void *user, uint8_t *buf, size_t n) {  // impl Read for &[u8]
+    SliceReader *s = (SliceReader *)user;
+    size_t k = std::min(n, s->len);
+    if (k) memcpy(buf, s->p, k);
+    s->p += k; s->len -= k;
+    return (long)k;
+}
+}  // namespace
+
+// decode_blocks (frame_decoder.rs:309-377).  `slice` != null selects decode_from_to's trailer rule (:505-516):
+// the checksum is taken only if its 4 bytes are present, otherwise left for the next call.
+static int fd_decode_blocks_impl(b200z_frame_decoder *d, b200z_read_fn rd, void *user, int strategy, size_t n, int *finished, SliceReader *slice) {
+    if (!d || !rd) return B200Z_ERR_INVALID_ARGUMENT;
+    if (!d->has_state) return fd_fail(d, B200Z_ERR_NOT_YET_INITIALIZED, 0);
+    if (d->state.status) return fd_fail(d, (int)(d->state.status & 0xffff), (int)((d->state.status >> 16) & 0xff));
+    const size_t buffer_size_before = fd_buffer_len(d);
+    const size_t block_counter_before = d->block_counter;
+    bool stop = false;
+    while (!stop) {
+        // gather blocks for one GPU submission.  All / UptoBlocks know where to stop from the headers alone;
+        // UptoBytes must see each block's decoded size, so it submits block by block.
+        Submission &s = d->sub;
+        s.clear();
+        d->staging.clear();
+        TableCursor cur;
+        cursor_from_carry(cur, d->carry, 0);
+        std::vector<uint64_t> bytes_after;  // bytes_read_counter after each gathered block
+        int pending_err = 0, pending_stage = 0;
+        bool saw_last = false;
+        uint64_t brc = d->bytes_read_counter;
+        size_t gathered_target = strategy == B200Z_STRATEGY_UPTO_BYTES ? 1 : (strategy == B200Z_STRATEGY_UPTO_BLOCKS ? std::max<size_t>(n, 1) - (d->block_counter - block_counter_before) : SIZE_MAX);
+        if (strategy == B200Z_STRATEGY_ALL) gathered_target = 4096;  // bound the staging buffer; loop continues
+        while (s.descs.size() < gathered_target) {
+            uint8_t hb[3];
+            if (!read_exact(rd, user, hb, 3)) { pending_err = B200Z_ERR_BLOCK_HEADER_READ; pending_stage = B200Z_STAGE_BLOCK_HEADER; break; }
+            BlockHeader bh;
+            int e = parse_block_header(hb, bh);
+            if (e) { pending_err = e; pending_stage = B200Z_STAGE_BLOCK_HEADER; break; }
+            brc += 3;
+            size_t off = d->staging.size();
+            d->staging.resize(off + bh.content_size);
+            if (!read_exact(rd, user, d->staging.data() + off, bh.content_size)) {
+                d->staging.resize(off);
+                pending_err = bh.type == BT_COMPRESSED ? B200Z_ERR_BLOCK_CONTENT_READ : B200Z_ERR_BLOCK_BODY_READ; pending_stage = B200Z_STAGE_BLOCK_BODY;
+                break;
+            }
+            BlockDesc bd;
+            memset(&bd, 0, sizeof bd);
+            BlockRefs r;
+            bd.src_off = off; bd.src_size = bh.content_size; bd.frame = 0; bd.btype = bh.type; bd.raw_size = bh.decompressed_size;
+            bd.block_in_frame = (uint32_t)(d->block_counter + s.descs.size()); bd.last = bh.last;
+            if (bh.type == BT_COMPRESSED) plan_compressed_block(d->staging.data() + off, bh.content_size, bd, r, cur, s.n_huf, s.n_fse, s.lit_bytes, s.nseq);
+            s.descs.push_back(bd); s.refs.push_back(r);
+            brc += bh.content_size;
+            bytes_after.push_back(brc);
+            if (bd.host_status) break;
+            if (bh.last) { saw_last = true; break; }
+        }
+        uint32_t failed = 0, done = 0;
+        int e = 0;
+        if (!s.descs.empty()) e = fd_submit(d, cur, &failed, &done);
+        // counters exactly as the reference leaves them (:325-343)
+        if (done > 0) d->bytes_read_counter = bytes_after[done - 1];
+        d->block_counter += done;
+        if (e) {
+            if (d->last_stage >= B200Z_STAGE_BLOCK_BODY && d->last_stage <= B200Z_STAGE_EXECUTE) d->bytes_read_counter += 3;
+            return fd_fail(d, e, d->last_stage);
+        }
+        if (pending_err) {
+            if (pending_stage == B200Z_STAGE_BLOCK_BODY) d->bytes_read_counter += 3;
+            d->state.status = mk_status((uint32_t)pending_err, (uint32_t)pending_stage);
+            return fd_fail(d, pending_err, pending_stage);
+        }
+        if (saw_last) {
+            d->frame_finished = true;
+            if (d->hdr.content_checksum() && !(slice && slice->len < 4)) {
+                uint8_t cs[4];
+                if (!read_exact(rd, user, cs, 4)) return fd_fail(d, B200Z_ERR_FAILED_TO_READ_CHECKSUM, B200Z_STAGE_CHECKSUM);
+                d->bytes_read_counter += 4;
+                d->check_sum = (uint32_t)cs[0] | ((uint32_t)cs[1] << 8) | ((uint32_t)cs[2] << 16) | ((uint32_t)cs[3] << 24);
+                d->has_check_sum = true;
+            }
+            break;
+        }
+        if (strategy == B200Z_STRATEGY_UPTO_BLOCKS) stop = d->block_counter - block_counter_before >= n;
+        else if (strategy == B200Z_STRATEGY_UPTO_BYTES) stop = fd_buffer_len(d) - buffer_size_before >= n;
+    }
+    d->last_stage = 0;
+    if (finished) *finished = d->frame_finished ? 1 : 0;
+    return 0;
+}
+
+extern "C" int b200z_frame_decoder_decode_blocks(b200z_frame_decoder *d, b200z_read_fn rd, void *user, int strategy, size_t n, int *finished) {
+    return fd_decode_blocks_impl(d, rd, user, strategy, n, finished, nullptr);
+}
+
+// drain `amount` bytes from the front of the device buffer into host memory / a writer; feeds the hash
+static long fd_drain(b200z_frame_decoder *d, size_t amount, uint8_t *target, b200z_write_fn wr, void *user) {
+    if (amount == 0) return 0;
+    b200z_ctx *c = d->ctx;
+    if (c->use()) return -1;
+    std::vector<uint8_t> tmp;
+    uint8_t *dst = target;
+    if (!dst) { tmp.resize(amount); dst = tmp.data(); }
+    if (cudaMemcpyAsync(dst, d->d_out.as<uint8_t>() + (d->drained - d->base), amount, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) { cudaGetLastError(); return -1; }
+    size_t written = amount;
+    bool failed = false;
+    if (!target) {  // write_all_bytes (decode_buffer.rs:318-328)
+        written = 0;
+        while (written < amount) {
+            long w = wr(user, dst + written, amount - written);
+            if (w == 0) break;
+            if (w < 0) { failed = true; break; }
+            written += (size_t)w;
+        }
+    }
+    d->hash.update(dst, written);
+    d->drained += written;
+    return failed ? -1 : (long)written;
+}
+
+extern "C" long b200z_frame_decoder_read(b200z_frame_decoder *d, uint8_t *buf, size_t len) {  // impl Read :615-627
+    if (!d || !d->has_state) return 0;
+    size_t amount = d->frame_finished ? std::min(len, fd_buffer_len(d)) : std::min(len, fd_can_drain_to_window(d));
+    return fd_drain(d, amount, buf, nullptr, nullptr);
+}
+extern "C" long b200z_frame_decoder_collect_to_writer(b200z_frame_decoder *d, b200z_write_fn wr, void *user) {  // :393-404
+    if (!d || !d->has_state || !wr) return 0;
+    size_t amount = fd_finished(d) ? fd_buffer_len(d) : fd_can_drain_to_window(d);
+    return fd_drain(d, amount, nullptr, wr, user);
+}
+extern "C" size_t b200z_frame_decoder_can_collect(const b200z_frame_decoder *d) {  // :409-424
+    if (!d || !d->has_state) return 0;
+    return fd_finished(d) ? fd_buffer_len(d) : fd_can_drain_to_window(d);
+}
+extern "C" int b200z_frame_decoder_is_finished(const b200z_frame_decoder *d) { return d ? fd_finished(d) : 1; }
+extern "C" size_t b200z_frame_decoder_blocks_decoded(const b200z_frame_decoder *d) { return d && d->has_state ? d->block_counter : 0; }
+extern "C" uint64_t b200z_frame_decoder_bytes_read_from_source(const b200z_frame_decoder *d) { return d && d->has_state ? d->bytes_read_counter : 0; }
+extern "C" uint64_t b200z_frame_decoder_content_size(const b200z_frame_decoder *d) { return d && d->has_state ? d->hdr.frame_content_size : 0; }
+extern "C" int b200z_frame_decoder_get_checksum_from_data(const b200z_frame_decoder *d, uint32_t *out) {
+    if (!d || !d->has_state || !d->has_check_sum) return 0;
+    *out = d->check_sum; return 1;
+}
+extern "C" int b200z_frame_decoder_get_calculated_checksum(const b200z_frame_decoder *d, uint32_t *out) {
+    if (!d || !d->has_state) return 0;
+    *out = (uint32_t)d->hash.digest(); return 1;
+}
+
+// decode_from_to (frame_decoder.rs:439-529): decodes as many WHOLE blocks as `src` holds
+extern "C" int b200z_frame_decoder_decode_from_to(b200z_frame_decoder *d, const uint8_t *src, size_t src_len, uint8_t *dst, size_t dst_len,
+                                                  size_t *read, size_t *written) {
+    if (!d || !read || !written) return B200Z_ERR_INVALID_ARGUMENT;
+    uint64_t at_start = d->has_state ? d->bytes_read_counter : 0;
+    if (!fd_finished(d) || !d->has_state) {
+        SliceReader mt{src, src_len};
+        if (!d->has_state) { int e = b200z_frame_decoder_init(d, slice_read, &mt); if (e) return e; }
+        if (d->hdr.content_checksum() && d->frame_finished && !d->has_check_sum) {  // :465-477
+            if (mt.len >= 4) {
+                d->bytes_read_counter += 4;
+                d->check_sum = (uint32_t)mt.p[0] | ((uint32_t)mt.p[1] << 8) | ((uint32_t)mt.p[2] << 16) | ((uint32_t)mt.p[3] << 24);
+                d->has_check_sum = true;
+            }
+            *read = 4; *written = 0;
+            return 0;
+        }
+        // the reference loops block by block while a whole block is present (:479-518); count them from the
+        // headers, then decode exactly those in one submission
+        size_t k = 0;
+        int hdr_err = 0;
+        {
+            SliceReader probe = mt;
+            while (probe.len >= 3) {
+                BlockHeader bh;
+                int e = parse_block_header(probe.p, bh);
+                if (e) { hdr_err = e; break; }
+                if (probe.len - 3 < bh.content_size) break;
+                probe.p += 3 + bh.content_size; probe.len -= 3 + bh.content_size;
+                k++;
+                if (bh.last) break;
+            }
+        }
+        if (k > 0) {
+            int e = fd_decode_blocks_impl(d, slice_read, &mt, B200Z_STRATEGY_UPTO_BLOCKS, k, nullptr, &mt);
+            if (e) return e;
+        }
+        if (hdr_err && !d->frame_finished) return fd_fail(d, hdr_err, B200Z_STAGE_BLOCK_HEADER);
+    }
+    long r = b200z_frame_decoder_read(d, dst, dst_len);
+    if (r < 0) return fd_fail(d, B200Z_ERR_FAILED_TO_DRAIN_DECODEBUFFER, B200Z_STAGE_DRAIN);
+    *written = (size_t)r;
+    *read = (size_t)(d->bytes_read_counter - at_start);
+    return 0;
+}
+
+// decode_all (frame_decoder.rs:541-577)
+extern "C" int b200z_frame_decoder_decode_all(b200z_frame_decoder *d, const uint8_t *input, size_t input_len, uint8_t *output, size_t output_cap, size_t *written) {
+    if (!d || !written) return B200Z_ERR_INVALID_ARGUMENT;
+    SliceReader in{input, input_len};
+    size_t total = 0;
+    while (in.len != 0) {
+        int e = b200z_frame_decoder_init(d, slice_read, &in);
+        if (e == B200Z_ERR_SKIP_FRAME) {
+            if ((size_t)d->skip_len > in.len) return fd_fail(d, B200Z_ERR_FAILED_TO_SKIP_FRAME, 0);
+            in.p += d->skip_len; in.len -= d->skip_len;
+            continue;
+        }
+        if (e) return e;
+        for (;;) {
+            if ((e = b200z_frame_decoder_decode_blocks(d, slice_read, &in, B200Z_STRATEGY_UPTO_BYTES, 1024 * 1024, nullptr))) return e;
+            long w = b200z_frame_decoder_read(d, output + total, output_cap - total);
+            if (w < 0) return fd_fail(d, B200Z_ERR_FAILED_TO_DRAIN_DECODEBUFFER, B200Z_STAGE_DRAIN);
+            total += (size_t)w;
+            if (b200z_frame_decoder_can_collect(d) != 0) return fd_fail(d, B200Z_ERR_TARGET_TOO_SMALL, 0);
+            if (fd_finished(d)) break;
+        }
+    }
+    *written = total;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// StreamingDecoder mirror (decoding/streaming_decoder.rs)
+// ---------------------------------------------------------------------------------------------------------------
+struct b200z_streaming_decoder {
+    b200z_frame_decoder *dec = nullptr;
+    bool owns = false;
+    b200z_read_fn rd = nullptr;
+    void *user = nullptr;
+};
+
+static int sd_make(b200z_frame_decoder *dec, bool owns, b200z_read_fn rd, void *user, b200z_streaming_decoder **out) {
+    int e = b200z_frame_decoder_init(dec, rd, user);
+    if (e) { if (owns) b200z_frame_decoder_free(dec); return e; }
+    b200z_streaming_decoder *s = new b200z_streaming_decoder();
+    s->dec = dec; s->owns = owns; s->rd = rd; s->user = user;
+    *out = s;
+    return 0;
+}
+extern "C" int b200z_streaming_decoder_new(b200z_ctx *c, b200z_read_fn rd, void *user, b200z_streaming_decoder **out) {
+    if (!c || !rd || !out) return B200Z_ERR_INVALID_ARGUMENT;
+    b200z_frame_decoder *dec = nullptr;
+    int e = b200z_frame_decoder_new(c, &dec);
+    if (e) return e;
+    return sd_make(dec, true, rd, user, out);
+}
+extern "C" int b200z_streaming_decoder_new_with_decoder(b200z_read_fn rd, void *user, b200z_frame_decoder *dec, b200z_streaming_decoder **out) {
+    if (!dec || !rd || !out) return B200Z_ERR_INVALID_ARGUMENT;
+    return sd_make(dec, false, rd, user, out);
+}
+extern "C" int b200z_streaming_decoder_new_with_max_window_size(b200z_ctx *c, b200z_read_fn rd, void *user, uint64_t mw, b200z_streaming_decoder **out) {
+    if (!c || !rd || !out) return B200Z_ERR_INVALID_ARGUMENT;
+    b200z_frame_decoder *dec = nullptr;
+    int e = b200z_frame_decoder_new(c, &dec);
+    if (e) return e;
+    b200z_frame_decoder_set_max_window_size(dec, mw);
+    return sd_make(dec, true, rd, user, out);
+}
+extern "C" long b200z_streaming_decoder_read(b200z_streaming_decoder *s, uint8_t *buf, size_t len, int *error) {  // :118-155
+    if (error) *error = 0;
+    if (!s) return -1;
+    b200z_frame_decoder *d = s->dec;
+    if (fd_finished(d) && b200z_frame_decoder_can_collect(d) == 0) return 0;
+    while (b200z_frame_decoder_can_collect(d) < len && !fd_finished(d)) {
+        size_t need = len - b200z_frame_decoder_can_collect(d);
+        int e = b200z_frame_decoder_decode_blocks(d, s->rd, s->user, B200Z_STRATEGY_UPTO_BYTES, need, nullptr);
+        if (e) { if (error) *error = e; return -1; }
+    }
+    return b200z_frame_decoder_read(d, buf, len);
+}
+extern "C" b200z_frame_decoder *b200z_streaming_decoder_frame_decoder(b200z_streaming_decoder *s) { return s ? s->dec : nullptr; }
+extern "C" b200z_frame_decoder *b200z_streaming_decoder_into_frame_decoder(b200z_streaming_decoder *s) {
+    if (!s) return nullptr;
+    b200z_frame_decoder *d = s->dec;
+    delete s;
+    return d;
+}
+extern "C" void b200z_streaming_decoder_free(b200z_streaming_decoder *s) {
+    if (!s) return;
+    if (s->owns) b200z_frame_decoder_free(s->dec);
+    delete s;
+}

@@ -1,0 +1,115 @@
+// b200z_types.h -- POD layouts shared by the host planner and the CUDA kernels.
+//
+// Data layout in HBM:
+//   input      : all frames of a submission, byte-for-byte as on the wire (never re-packed)
+//   BlockDesc  : one 128-byte descriptor per zstd block, written by the host planner (plan.cpp)
+//   HufSlot    : GPU-resident huff0 LUT (ruzstd huff0::HuffmanTable.decode, huff0_decoder.rs:57-74)
+//   FseTab     : GPU-resident FSE LUT (ruzstd fse::FSETable.decode, fse_decoder.rs:59-83), one per LL/OF/ML
+//   literals   : scratch, regenerated literals of every Compressed/Treeless literals section
+//   sequences  : scratch, 3 x u32 {ll, ml, of} per sequence (ruzstd blocks::sequence_section::Sequence)
+//   output     : plaintext, each frame at the caller's out_off
+#pragma once
+#include <stdint.h>
+
+namespace b200z {
+
+// ---- block types / literal types as on the wire (block_decoder.rs:259-268, literals_section.rs:226-235)
+enum : uint32_t { BT_RAW = 0, BT_RLE = 1, BT_COMPRESSED = 2 };
+enum : uint32_t { LT_RAW = 0, LT_RLE = 1, LT_COMPRESSED = 2, LT_TREELESS = 3 };
+// sequence compression modes (blocks/sequence_section.rs:49-63)
+enum : uint32_t { MODE_PREDEFINED = 0, MODE_RLE = 1, MODE_FSE = 2, MODE_REPEAT = 3 };
+
+constexpr uint32_t HUF_MAX_BITS = 11;         // huff0_decoder.rs:9
+constexpr uint32_t HUF_TABLE_ENTRIES = 2048;  // 1 << 11
+constexpr uint32_t FSE_MAX_ENTRIES = 512;     // LL/ML max log 9 (sequence_section_decoder.rs:288-292)
+
+// huff0 LUT: entry = symbol | num_bits << 8   (huff0_decoder.rs:389-394 Entry{symbol,num_bits})
+struct alignas(16) HufSlot {
+    uint32_t max_bits;  // 0 = uninitialised (literals_section_decoder.rs:61-63)
+    uint32_t status;    // build error (b200z_error) or 0
+    uint32_t pad[2];
+    uint16_t e[HUF_TABLE_ENTRIES];
+};
+
+// FSE LUT: entry = base_line | num_bits << 16 | symbol << 24   (fse_decoder.rs:312-320 Entry)
+// An RLE mode is stored as log = 0, e[0] = {0, 0, symbol}: reading 0 bits always lands on entry 0, which is
+// what decode_sequences_with_rle does by substituting the constant code (sequence_section_decoder.rs:74-88).
+struct alignas(16) FseTab {
+    uint32_t log;     // accuracy_log, 0 for RLE
+    uint32_t valid;   // 0 = never built (FSEDecoderError::TableIsUninitialized, fse_decoder.rs:33-35)
+    uint32_t is_rle;
+    uint32_t pad;
+    uint32_t e[FSE_MAX_ENTRIES];
+};
+struct alignas(16) FseSlot { FseTab ll, of, ml; };
+
+__host__ __device__ inline uint32_t fse_pack(uint32_t base, uint32_t nb, uint32_t sym) { return base | (nb << 16) | (sym << 24); }
+
+// One descriptor per block; everything the reference derives in decompress_block before calling the three hot
+// stages (block_decoder.rs:97-181): literals header fields, sequence header fields, where each payload starts,
+// and which table every section decodes with (Treeless / Repeat resolved to the defining slot by the planner).
+struct alignas(16) BlockDesc {
+    uint64_t src_off;        // offset of the block CONTENT in the input buffer (after the 3-byte header)
+    uint64_t lit_buf_off;    // offset into the literals scratch (Compressed/Treeless literals only)
+    uint64_t seq_buf_off;    // offset into the sequence scratch, in sequences
+    uint32_t src_size;       // Block_Size (content bytes; 1 for RLE)
+    uint32_t frame;          // index of the owning frame in this submission
+    uint32_t btype;          // BT_*
+    uint32_t raw_size;       // Raw/RLE: decompressed size
+    uint32_t lit_type;       // LT_*
+    uint32_t nstreams;       // 1 or 4 (Compressed/Treeless)
+    uint32_t regen_size;     // literals regenerated size
+    uint32_t lit_comp_size;  // literals compressed size (incl. tree description and jump table)
+    uint32_t lit_off;        // offset of the literals payload inside the block content
+    uint32_t seq_off;        // offset of the sequences payload (after the 1-4 byte header) inside the block content
+    uint32_t nseq;           // number of sequences
+    uint32_t modes;          // compression modes byte
+    uint32_t host_status;    // error the planner found for this block (stage in bits 16..23), 0 = none
+    uint32_t block_in_frame; // ordinal of the block inside its frame
+    uint32_t last;           // last block of the frame
+    uint32_t pad0;
+    const HufSlot *huf;      // table the literals decode with (own slot when lit_type == LT_COMPRESSED)
+    HufSlot *huf_build;      // where a new Huffman table is built, or null
+    const FseTab *ll, *of, *ml;  // tables the sequences decode with (null = uninitialised)
+    FseSlot *fse_build;      // where new LL/OF/ML tables (FSE or RLE modes) are built, or null
+};
+
+// Per-block results written by the kernels
+struct alignas(16) BlockAux {
+    uint32_t status;         // first error of this block: code | stage << 16, 0 = ok
+    uint32_t out_size;       // decompressed size of the block (known after sequence decode)
+    uint32_t lit_streams_off;// offset inside the block content where the jump table / single stream starts
+    uint32_t seq_bits_off;   // offset inside the block content where the sequence bitstream starts
+    uint64_t out_off;        // position of the block inside its frame's output (after the scan)
+    uint32_t sum_ll;         // sum of literal lengths over the block's sequences
+    uint32_t pad;
+};
+
+// Per-frame state: carried between submissions for the streaming mirror, fresh for batch frames.
+// offset_hist: scratch.rs:22,44 ; total_output_counter: decode_buffer.rs:14 ; produced/drained give
+// DecodeBuffer::len() (decode_buffer.rs:58) = produced - drained.
+struct alignas(16) FrameState {
+    uint32_t hist[3];
+    uint32_t status;          // first error: code | stage << 16
+    uint64_t produced;        // bytes of this frame written to the output buffer so far
+    uint64_t drained;         // bytes the host already drained (streaming); offsets reach back to `drained`
+    uint64_t counter;         // total_output_counter (quirk: Raw/RLE blocks and fully-in-dict matches not counted)
+    uint32_t error_block;     // block_in_frame of the failing block
+    uint32_t blocks_done;     // blocks fully executed
+};
+
+struct alignas(16) FrameDesc {
+    uint64_t out_off;         // where the frame's byte 0 lives in the output buffer
+    uint64_t out_cap;         // room at out_off
+    uint64_t window_size;
+    const uint8_t *dict;      // dictionary content (device) or null
+    uint64_t dict_len;
+    uint32_t first_block;
+    uint32_t nblocks;
+    uint32_t host_status;     // planner error that ends the frame after `nblocks` blocks (code | stage << 16)
+    uint32_t pad;
+};
+
+__host__ __device__ inline uint32_t mk_status(uint32_t code, uint32_t stage) { return code | (stage << 16); }
+
+}  // namespace b200z

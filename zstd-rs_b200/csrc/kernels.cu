@@ -1,0 +1,460 @@
+// kernels.cu -- sm_100a kernels of the zstd block-decompression hot path.
+//
+//   k_predefined : the three predefined FSE LUTs, built once per context
+//   k_setup      : per block: Huffman tree description -> huff0 LUT, FSE table descriptions -> LL/OF/ML LUTs
+//                  (HuffmanTable::build_decoder huff0_decoder.rs:117, maybe_update_fse_tables
+//                  sequence_section_decoder.rs:294-410)
+//   k_huf        : literals: one lane per huff0 stream (decompress_literals literals_section_decoder.rs:40-158)
+//   k_fse        : sequences: one lane per block walks the reversed bitstream with three interleaved FSE states
+//                  (decode_sequences sequence_section_decoder.rs:14-221)
+//   k_exec       : LZ77 execution into the frame's output (execute_sequences sequence_execution.rs:5-118,
+//                  DecodeBuffer::{push,repeat,repeat_from_dict} decode_buffer.rs:74-179), one warp per frame,
+//                  blocks of a frame in order
+//
+// Integer/byte work only; the roofline is HBM bandwidth.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+#include "tables.cuh"
+
+namespace b200z {
+
+// ------------------------------------------------------------------------------------------------------------
+// Reversed bit reader over global memory (the device form of BitReaderReversed, bit_reader_reverse.rs:6-162):
+// left-aligned 64-bit container refilled with ALIGNED 32-bit words walking down the stream; bits below the
+// stream start read as zero and `p` (bits remaining) goes negative, like bits_remaining() (:27-29).
+// ------------------------------------------------------------------------------------------------------------
+struct RevBits {
+    const uint32_t *base;  // 4-byte aligned address at or below the stream start
+    uint64_t cont;         // unread bits, left aligned
+    int32_t fill;          // bits loaded in cont (virtual zeros below the stream start count)
+    int32_t wi;            // words [0, wi) not fetched yet
+    uint32_t g0;           // bit offset of the stream's first byte inside word 0
+    int32_t p;             // bits_remaining()
+
+    // Position right below the end-of-stream marker.  Returns false for "ExtraPadding" (no 1 bit in the last
+    // byte, or an empty stream): the callers' skip loops (literals_section_decoder.rs:97-109 etc.) give up
+    // after 8 zero bits.
+    __device__ __forceinline__ bool init(const uint8_t *src, uint32_t len) {
+        if (len == 0) return false;
+        uint32_t last = src[len - 1];
+        if (last == 0) return false;
+        uintptr_t a = (uintptr_t)src;
+        base = (const uint32_t *)(a & ~(uintptr_t)3);
+        g0 = (uint32_t)(a & 3) * 8u;
+        p = (int32_t)((len - 1) * 8u + (31u - (uint32_t)__clz((int)last)));  // data bits below the marker
+        cont = 0; fill = 0; wi = 0;
+        if (p > 0) {
+            uint32_t gtop = g0 + (uint32_t)p - 1u;  // global bit index of the first data bit
+            wi = (int32_t)(gtop >> 5);
+            uint32_t w = __ldg(base + wi);
+            if (wi == 0) w &= ~((1u << g0) - 1u);
+            uint32_t used = (gtop & 31u) + 1u;
+            cont = (uint64_t)w << (64u - used);
+            fill = (int32_t)used;
+        }
+        return true;
+    }
+    __device__ __forceinline__ void refill() {  // afterwards fill > 32
+        if (fill <= 32) {
+            uint32_t w = 0;
+            if (wi > 0) {
+                --wi;
+                w = __ldg(base + wi);
+                if (wi == 0) w &= ~((1u << g0) - 1u);
+            }
+            cont |= (uint64_t)w << (32 - fill);
+            fill += 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t get(uint32_t n) {  // n <= 32, needs fill >= n
+        uint32_t v = (uint32_t)((cont >> 1) >> (63u - n));
+        cont <<= n;
+        fill -= (int32_t)n;
+        p -= (int32_t)n;
+        return v;
+    }
+    __device__ __forceinline__ uint32_t peek(uint32_t n) const { return (uint32_t)((cont >> 1) >> (63u - n)); }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_predefined(FseSlot *predef) {
+    uint32_t k = threadIdx.x;
+    if (k < 3) fse_build_predefined(k, k == 0 ? &predef->ll : (k == 1 ? &predef->of : &predef->ml));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_setup: one thread per block.
+// ------------------------------------------------------------------------------------------------------------
+__device__ int setup_one_seq_table(uint32_t mode, const uint8_t *&p, uint32_t &rem, uint32_t max_log, uint32_t max_sym,
+                                   FseTab *tab, int missing_err) {
+    if (mode == MODE_FSE) {
+        uint32_t used = 0;
+        int e = fse_build_decoder(p, rem, max_log, max_sym, tab, used);
+        if (e) return e;
+        p += used; rem -= used;  // used <= rem: the forward reader never reads past the slice
+    } else if (mode == MODE_RLE) {
+        if (rem == 0) return missing_err;
+        uint32_t sym = p[0];
+        if (sym > max_sym) return B200Z_ERR_SEQ_MISSING_BYTE_FOR_RLE_ML_TABLE;  // sic, sequence_section_decoder.rs:321,356,391
+        tab->log = 0; tab->valid = 1; tab->is_rle = 1; tab->e[0] = fse_pack(0, 0, sym);
+        p += 1; rem -= 1;
+    }
+    return 0;
+}
+
+__global__ void k_setup(const BlockDesc *__restrict__ descs, BlockAux *__restrict__ aux, const uint8_t *__restrict__ input, uint32_t nblocks) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    const BlockDesc &d = descs[b];
+    BlockAux a;
+    a.status = 0; a.out_size = 0; a.lit_streams_off = 0; a.seq_bits_off = 0; a.out_off = 0; a.sum_ll = 0; a.pad = 0;
+    uint32_t st_lit = 0, st_seq = 0;
+    if (d.btype == BT_COMPRESSED && !(d.host_status && (d.host_status >> 24) == 1)) {
+        const uint8_t *content = input + d.src_off;
+        if (d.lit_type == LT_COMPRESSED) {
+            uint32_t used = 0;
+            int e = huf_build_decoder(content + d.lit_off, d.lit_comp_size, d.huf_build, used);
+            if (e) st_lit = mk_status((uint32_t)e, B200Z_STAGE_LITERALS);
+            a.lit_streams_off = used;
+        } else if (d.lit_type == LT_TREELESS) {
+            if (d.huf == nullptr) st_lit = mk_status(B200Z_ERR_LIT_UNINITIALIZED_HUFFMAN_TABLE, B200Z_STAGE_LITERALS);
+        }
+        if (d.nseq != 0 && !d.host_status) {
+            const uint8_t *p = content + d.seq_off;
+            uint32_t rem = d.src_size - d.seq_off;
+            int e = setup_one_seq_table(d.modes >> 6, p, rem, 9, 35, d.fse_build ? &d.fse_build->ll : nullptr, B200Z_ERR_SEQ_MISSING_BYTE_FOR_RLE_LL_TABLE);
+            if (!e) e = setup_one_seq_table((d.modes >> 4) & 3, p, rem, 8, 31, d.fse_build ? &d.fse_build->of : nullptr, B200Z_ERR_SEQ_MISSING_BYTE_FOR_RLE_OF_TABLE);
+            if (!e) e = setup_one_seq_table((d.modes >> 2) & 3, p, rem, 9, 52, d.fse_build ? &d.fse_build->ml : nullptr, B200Z_ERR_SEQ_MISSING_BYTE_FOR_RLE_ML_TABLE);
+            if (e) st_seq = mk_status((uint32_t)e, B200Z_STAGE_SEQUENCES);
+            a.seq_bits_off = (uint32_t)(p - content);
+        }
+    }
+    a.status = st_lit;   // literals-stage status; sequence-stage status kept separately in `pad` until k_fse merges
+    a.pad = st_seq;
+    aux[b] = a;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_huf: literals.
+// ------------------------------------------------------------------------------------------------------------
+// Decode one huff0 stream: symbols are emitted while the bits consumed by emitted symbols are < the stream's
+// data bits (literals_section_decoder.rs:112-115: `while bits_remaining > -max_num_bits`), at most `cap`.
+// Returns: 0 = stream exhausted exactly, 1 = exhausted but over-read (BitstreamReadMismatch for 4 streams),
+// 2 = cap reached before exhaustion, 3 = ExtraPadding.
+__device__ __forceinline__ int huf_stream(const uint16_t *__restrict__ tab, uint32_t mb, const uint8_t *src, uint32_t len,
+                                          uint8_t *dst, uint32_t store_limit, uint32_t cap, uint32_t &count) {
+    RevBits br;
+    count = 0;
+    if (!br.init(src, len)) return 3;
+    uint32_t n = 0;
+    while (br.p > 0) {
+        if (n == cap) { count = n; return 2; }
+        br.refill();
+        uint32_t e = tab[br.peek(mb)];
+        if (n < store_limit) dst[n] = (uint8_t)e;
+        n++;
+        br.get(e >> 8);
+    }
+    count = n;
+    return br.p == 0 ? 0 : 1;
+}
+
+__global__ void k_huf(const BlockDesc *__restrict__ descs, BlockAux *__restrict__ aux, const uint8_t *__restrict__ input,
+                      uint8_t *__restrict__ lit_scratch, uint32_t nblocks) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t b = t >> 2, k = t & 3;
+    bool active = b < nblocks;
+    uint32_t err = 0;
+    bool work = false;
+    const BlockDesc *d = nullptr;
+    if (active) {
+        d = &descs[b];
+        work = d->btype == BT_COMPRESSED && (d->lit_type == LT_COMPRESSED || d->lit_type == LT_TREELESS) &&
+               !(d->host_status && (d->host_status >> 24) == 1) && aux[b].status == 0;
+    }
+    // all four lanes of a group take the same branches up to the per-stream decode
+    int rc = 0; uint32_t count = 0; bool irregular = false;
+    const uint8_t *payload = nullptr; uint32_t plen = 0; const HufSlot *slot = nullptr; uint8_t *dst = nullptr;
+    uint32_t j1 = 0, j2 = 0, j3 = 0;
+    if (work) {
+        slot = d->huf;
+        uint32_t so = aux[b].lit_streams_off;
+        payload = input + d->src_off + d->lit_off + so;
+        plen = d->lit_comp_size - so;
+        dst = lit_scratch + d->lit_buf_off;
+        if (slot == nullptr || slot->max_bits == 0) { err = B200Z_ERR_LIT_UNINITIALIZED_HUFFMAN_TABLE; work = false; }
+    }
+    if (work) {
+        uint32_t mb = slot->max_bits, regen = d->regen_size;
+        if (d->nstreams == 4) {
+            if (plen < 6) { err = B200Z_ERR_LIT_MISSING_BYTES_FOR_JUMP_HEADER; }
+            else {
+                j1 = payload[0] | (payload[1] << 8); j2 = j1 + (payload[2] | (payload[3] << 8)); j3 = j2 + (payload[4] | (payload[5] << 8));
+                if (plen - 6 < j3) err = B200Z_ERR_LIT_MISSING_BYTES_FOR_LITERALS;
+            }
+            if (!err) {
+                const uint8_t *s0 = payload + 6;
+                uint32_t S = (regen + 3) >> 2;
+                // fast path: the standard split -- streams 0..2 regenerate S bytes, stream 3 the rest
+                if (regen >= 3 * S) {
+                    uint32_t off[5] = {0, j1, j2, j3, plen - 6};
+                    uint32_t cap = k < 3 ? S : regen - 3 * S;
+                    rc = huf_stream(slot->e, mb, s0 + off[k], off[k + 1] - off[k], dst + k * S, cap, cap, count);
+                    irregular = (rc != 0) || (count != cap);
+                } else irregular = true;
+                // any anomaly in the group -> lane 0 replays the block with the reference's exact semantics
+                uint32_t gmask = 0xFu << (threadIdx.x & 28u & 31u);
+                bool any = __any_sync(gmask, irregular);
+                if (any && k == 0) {
+                    uint32_t off[5] = {0, j1, j2, j3, plen - 6};
+                    uint32_t total = 0;
+                    for (uint32_t s = 0; s < 4 && !err; s++) {
+                        uint32_t c = 0;
+                        uint32_t lim = total < regen ? regen - total : 0;
+                        int r = huf_stream(slot->e, mb, s0 + off[s], off[s + 1] - off[s], dst + (total < regen ? total : regen), lim, 0xFFFFFFFFu, c);
+                        if (r == 3) err = B200Z_ERR_LIT_EXTRA_PADDING;
+                        else if (r == 1) err = B200Z_ERR_LIT_BITSTREAM_READ_MISMATCH;
+                        total += c;
+                    }
+                    if (!err && total != regen) err = B200Z_ERR_LIT_DECODED_LITERAL_COUNT_MISMATCH;
+                }
+            }
+        } else if (k == 0) {
+            // single stream: no exact-landing check (literals_section_decoder.rs:143-147), only the total count
+            rc = huf_stream(slot->e, mb, payload, plen, dst, regen, 0xFFFFFFFFu, count);
+            if (rc == 3) err = B200Z_ERR_LIT_EXTRA_PADDING;
+            else if (count != regen) err = B200Z_ERR_LIT_DECODED_LITERAL_COUNT_MISMATCH;
+        }
+    }
+    if (active && k == 0 && err) aux[b].status = mk_status(err, B200Z_STAGE_LITERALS);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_fse: sequences.  One lane per block.
+// ------------------------------------------------------------------------------------------------------------
+__constant__ uint32_t c_ll_base[36] = {0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,18,20,22,24,28,32,40,48,64,128,256,512,1024,2048,4096,8192,16384,32768,65536};
+__constant__ uint8_t c_ll_bits[36] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,6,7,8,9,10,11,12,13,14,15,16};
+__constant__ uint32_t c_ml_base[53] = {3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,30,31,32,33,34,35,37,39,41,43,47,51,59,67,83,99,131,259,515,1027,2051,4099,8195,16387,32771,65539};
+__constant__ uint8_t c_ml_bits[53] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,4,5,7,8,9,10,11,12,13,14,15,16};
+
+__global__ void k_fse(const BlockDesc *__restrict__ descs, BlockAux *__restrict__ aux, const uint8_t *__restrict__ input,
+                      uint32_t *__restrict__ seq_scratch, uint32_t nblocks) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    const BlockDesc &d = descs[b];
+    uint32_t st_seq = aux[b].pad;
+    aux[b].pad = 0;
+    if (d.btype != BT_COMPRESSED) { aux[b].out_size = d.raw_size; return; }
+    if (d.host_status) return;
+    if (d.nseq == 0) { aux[b].out_size = d.regen_size; return; }
+    uint32_t err = 0;
+    uint64_t sum_ml = 0, sum_ll = 0;
+    if (st_seq == 0) {
+        const uint8_t *src = input + d.src_off + aux[b].seq_bits_off;
+        uint32_t len = d.src_size - aux[b].seq_bits_off;
+        RevBits br;
+        const FseTab *tl = d.ll, *to = d.of, *tm = d.ml;
+        uint32_t sl = 0, so = 0, sm = 0;
+        if (!br.init(src, len)) err = B200Z_ERR_SEQ_EXTRA_PADDING;
+        // init order LL, OF, ML (sequence_section_decoder.rs:164-166); an RLE'd component reads 0 bits
+        if (!err) { if (!tl || !tl->valid) err = B200Z_ERR_FSE_TABLE_IS_UNINITIALIZED; else { br.refill(); sl = tl->e[br.get(tl->log)]; } }
+        if (!err) { if (!to || !to->valid) err = B200Z_ERR_FSE_TABLE_IS_UNINITIALIZED; else { br.refill(); so = to->e[br.get(to->log)]; } }
+        if (!err) { if (!tm || !tm->valid) err = B200Z_ERR_FSE_TABLE_IS_UNINITIALIZED; else { br.refill(); sm = tm->e[br.get(tm->log)]; } }
+        uint32_t *out = seq_scratch + d.seq_buf_off * 3;
+        const uint32_t nseq = d.nseq;
+        for (uint32_t i = 0; i < nseq && !err; i++) {
+            uint32_t ll_code = sl >> 24, ml_code = sm >> 24, of_code = so >> 24;
+            if (ll_code > 35 || ml_code > 52) { err = B200Z_ERR_REFERENCE_WOULD_PANIC; break; }  // unreachable!: tables cap the symbols
+            if (of_code > 31) { err = B200Z_ERR_SEQ_UNSUPPORTED_OFFSET; break; }
+            uint32_t ll_bits = c_ll_bits[ll_code], ml_bits = c_ml_bits[ml_code];
+            // extra bits in the order OF, ML, LL (get_bits_triple, :185)
+            br.refill(); uint32_t obits = br.get(of_code);
+            br.refill(); uint32_t ml_add = br.get(ml_bits); uint32_t ll_add = br.get(ll_bits);
+            uint32_t offset = obits + (1u << of_code);
+            uint32_t ll = c_ll_base[ll_code] + ll_add, ml = c_ml_base[ml_code] + ml_add;
+            out[3 * i] = ll; out[3 * i + 1] = ml; out[3 * i + 2] = offset;
+            sum_ll += ll; sum_ml += ml;
+            if (i + 1 < nseq) {  // state updates in the order LL, ML, OF (:198-207)
+                br.refill();
+                sl = tl->e[(sl & 0xffffu) + br.get((sl >> 16) & 0xffu)];
+                sm = tm->e[(sm & 0xffffu) + br.get((sm >> 16) & 0xffu)];
+                so = to->e[(so & 0xffffu) + br.get((so >> 16) & 0xffu)];
+            }
+            if (br.p < 0) err = B200Z_ERR_SEQ_NOT_ENOUGH_BYTES_FOR_NUM_SEQUENCES;
+        }
+        if (!err && br.p > 0) err = B200Z_ERR_SEQ_EXTRA_BITS;
+        if (err) st_seq = mk_status(err, B200Z_STAGE_SEQUENCES);
+    }
+    aux[b].pad = st_seq;
+    aux[b].sum_ll = (uint32_t)(sum_ll > 0xffffffffull ? 0xffffffffull : sum_ll);
+    uint64_t total = sum_ml + d.regen_size;
+    aux[b].out_size = (uint32_t)(total > 0xffffffffull ? 0xffffffffull : total);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_exec: one warp per frame; blocks in order.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint32_t n, uint32_t lane) {
+    for (uint32_t k = lane; k < n; k += 32) dst[k] = src[k];
+}
+__device__ __forceinline__ void warp_fill(uint8_t *dst, uint8_t v, uint32_t n, uint32_t lane) {
+    for (uint32_t k = lane; k < n; k += 32) dst[k] = v;
+}
+// LZ77 match copy with byte-order-preserving overlap: byte k comes from src[k mod off] (repeat_in_chunks,
+// decode_buffer.rs:113-141: chunks of `offset` bytes re-read what the previous chunk wrote)
+__device__ __forceinline__ void warp_match(uint8_t *dst, const uint8_t *src, uint32_t n, uint32_t off, uint32_t lane) {
+    if (off >= n) { for (uint32_t k = lane; k < n; k += 32) dst[k] = src[k]; }
+    else { for (uint32_t k = lane; k < n; k += 32) dst[k] = src[k % off]; }
+}
+
+__global__ void k_exec(const BlockDesc *__restrict__ descs, const BlockAux *__restrict__ aux, const FrameDesc *__restrict__ frames,
+                       FrameState *__restrict__ states, const uint8_t *__restrict__ input, const uint8_t *__restrict__ lit_scratch,
+                       const uint32_t *__restrict__ seq_scratch, uint8_t *__restrict__ output, uint64_t output_cap, uint32_t nframes) {
+    uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    if (f >= nframes) return;
+    const FrameDesc &fd = frames[f];
+    FrameState st = states[f];
+    uint32_t h0 = st.hist[0], h1 = st.hist[1], h2 = st.hist[2];
+    uint64_t produced = st.produced, counter = st.counter;
+    const uint64_t drained = st.drained;
+    uint64_t cap = fd.out_cap;
+    if (fd.out_off > output_cap) cap = 0; else if (cap > output_cap - fd.out_off) cap = output_cap - fd.out_off;
+    uint8_t *out = output + fd.out_off;
+    uint32_t status = st.status, err_block = st.error_block, blocks_done = st.blocks_done;
+
+    for (uint32_t bi = 0; bi < fd.nblocks && !status; bi++) {
+        const uint32_t b = fd.first_block + bi;
+        const BlockDesc &d = descs[b];
+        // first error in the reference's order: header-level planner errors, literals, sequence header (planner),
+        // sequence tables + decode, then execution
+        uint32_t hs = d.host_status, hpos = hs >> 24;
+        hs &= 0x00ffffffu;
+        uint32_t bs = 0;
+        if (hs && hpos == 1) bs = hs;
+        else if (aux[b].status) bs = aux[b].status;
+        else if (hs) bs = hs;
+        else if (aux[b].pad) bs = aux[b].pad;
+        if (bs) { status = bs; err_block = d.block_in_frame; break; }
+
+        if (d.btype == BT_RAW) {
+            if (produced + d.raw_size > cap) { status = mk_status(B200Z_ERR_TARGET_TOO_SMALL, B200Z_STAGE_DRAIN); err_block = d.block_in_frame; break; }
+            warp_copy(out + produced, input + d.src_off, d.raw_size, lane);
+            produced += d.raw_size;   // extend_from_reader: total_output_counter untouched (decode_buffer.rs:66-72)
+        } else if (d.btype == BT_RLE) {
+            if (produced + d.raw_size > cap) { status = mk_status(B200Z_ERR_TARGET_TOO_SMALL, B200Z_STAGE_DRAIN); err_block = d.block_in_frame; break; }
+            warp_fill(out + produced, input[d.src_off], d.raw_size, lane);
+            produced += d.raw_size;
+        } else {
+            const uint8_t *lit;
+            uint32_t lit_rle = 0; uint8_t rle_byte = 0;
+            if (d.lit_type == LT_RAW) lit = input + d.src_off + d.lit_off;
+            else if (d.lit_type == LT_RLE) { lit = nullptr; lit_rle = 1; rle_byte = input[d.src_off + d.lit_off]; }
+            else lit = lit_scratch + d.lit_buf_off;
+            const uint32_t regen = d.regen_size;
+            uint32_t litpos = 0, e = 0;
+            const uint32_t *seqs = seq_scratch + d.seq_buf_off * 3;
+            for (uint32_t base = 0; base < d.nseq && !e; base += 32) {
+                uint32_t nb = d.nseq - base < 32 ? d.nseq - base : 32;
+                uint32_t my_ll = 0, my_ml = 0, my_of = 0;
+                if (lane < nb) { const uint32_t *s = seqs + (uint64_t)(base + lane) * 3; my_ll = s[0]; my_ml = s[1]; my_of = s[2]; }
+                for (uint32_t j = 0; j < nb; j++) {
+                    uint32_t ll = __shfl_sync(0xffffffffu, my_ll, j), ml = __shfl_sync(0xffffffffu, my_ml, j), of = __shfl_sync(0xffffffffu, my_of, j);
+                    if (ll > 0) {
+                        if ((uint64_t)litpos + ll > regen) { e = B200Z_ERR_EXEC_NOT_ENOUGH_BYTES_FOR_SEQUENCE; break; }
+                        if (produced + ll > cap) { e = B200Z_ERR_TARGET_TOO_SMALL; break; }
+                        if (lit_rle) warp_fill(out + produced, rle_byte, ll, lane); else warp_copy(out + produced, lit + litpos, ll, lane);
+                        litpos += ll; produced += ll; counter += ll;
+                    }
+                    // do_offset_history (sequence_execution.rs:59-118)
+                    uint32_t actual;
+                    if (ll > 0) {
+                        if (of == 1) actual = h0;
+                        else if (of == 2) { actual = h1; h1 = h0; h0 = actual; }
+                        else if (of == 3) { actual = h2; h2 = h1; h1 = h0; h0 = actual; }
+                        else { actual = of - 3; h2 = h1; h1 = h0; h0 = actual; }
+                    } else {
+                        if (of == 1) { actual = h1; h1 = h0; h0 = actual; }
+                        else if (of == 2) { actual = h2; h2 = h1; h1 = h0; h0 = actual; }
+                        else if (of == 3) { actual = h0 ? h0 - 1 : 0; h2 = h1; h1 = h0; h0 = actual; }
+                        else { actual = of - 3; h2 = h1; h1 = h0; h0 = actual; }
+                    }
+                    if (actual == 0) { e = B200Z_ERR_EXEC_ZERO_OFFSET; break; }
+                    if (ml > 0) {
+                        if (produced + ml > cap) { e = B200Z_ERR_TARGET_TOO_SMALL; break; }
+                        __syncwarp();
+                        uint64_t buf_len = produced - drained;
+                        if ((uint64_t)actual > buf_len) {
+                            // repeat_from_dict (decode_buffer.rs:143-179)
+                            if (counter <= fd.window_size) {
+                                uint64_t from_dict = (uint64_t)actual - buf_len;
+                                if (from_dict > fd.dict_len) { e = B200Z_ERR_EXEC_NOT_ENOUGH_BYTES_IN_DICTIONARY; break; }
+                                if (from_dict < ml) {
+                                    warp_copy(out + produced, fd.dict + fd.dict_len - from_dict, (uint32_t)from_dict, lane);
+                                    produced += from_dict; counter += from_dict;
+                                    __syncwarp();
+                                    uint32_t rest = ml - (uint32_t)from_dict;
+                                    uint64_t bl2 = produced - drained;  // repeat(self.buffer.len(), rest): from the buffer start
+                                    warp_match(out + produced, out + drained, rest, bl2 > 0xffffffffull ? 0xffffffffu : (uint32_t)bl2, lane);
+                                    produced += rest; counter += rest;
+                                } else {
+                                    warp_copy(out + produced, fd.dict + fd.dict_len - from_dict, ml, lane);
+                                    produced += ml;  // sic: total_output_counter not advanced on this branch (:166-171)
+                                }
+                            } else { e = B200Z_ERR_EXEC_OFFSET_TOO_BIG; break; }
+                        } else {
+                            warp_match(out + produced, out + produced - actual, ml, actual, lane);
+                            produced += ml; counter += ml;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            if (!e && litpos < regen) {
+                uint32_t rest = regen - litpos;
+                if (produced + rest > cap) e = B200Z_ERR_TARGET_TOO_SMALL;
+                else {
+                    if (lit_rle) warp_fill(out + produced, rle_byte, rest, lane); else warp_copy(out + produced, lit + litpos, rest, lane);
+                    produced += rest; counter += rest;
+                }
+            }
+            if (e) { status = mk_status(e, e == B200Z_ERR_TARGET_TOO_SMALL ? B200Z_STAGE_DRAIN : B200Z_STAGE_EXECUTE); err_block = d.block_in_frame; break; }
+        }
+        __syncwarp();
+        blocks_done++;
+    }
+    if (!status && fd.host_status) { status = fd.host_status & 0x00ffffffu; err_block = blocks_done; }
+    if (lane == 0) {
+        FrameState &o = states[f];
+        o.hist[0] = h0; o.hist[1] = h1; o.hist[2] = h2;
+        o.status = status; o.produced = produced; o.counter = counter; o.error_block = err_block; o.blocks_done = blocks_done;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------------------
+static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+int launch_predefined(FseSlot *predef, cudaStream_t s) {
+    k_predefined<<<1, 32, 0, s>>>(predef);
+    return (int)cudaGetLastError();
+}
+
+int launch_pipeline(const PipelineArgs &a, cudaStream_t s) {
+    if (a.nblocks) {
+        k_setup<<<cdiv(a.nblocks, 64), 64, 0, s>>>(a.descs, a.aux, a.input, a.nblocks);
+        k_huf<<<cdiv(a.nblocks * 4, 128), 128, 0, s>>>(a.descs, a.aux, a.input, a.lit_scratch, a.nblocks);
+        k_fse<<<cdiv(a.nblocks, 32), 32, 0, s>>>(a.descs, a.aux, a.input, a.seq_scratch, a.nblocks);
+    }
+    if (a.nframes)
+        k_exec<<<cdiv(a.nframes * 32, 128), 128, 0, s>>>(a.descs, a.aux, a.frames, a.states, a.input, a.lit_scratch, a.seq_scratch,
+                                                        a.output, a.output_cap, a.nframes);
+    return (int)cudaGetLastError();
+}
+
+uint32_t pipeline_launch_count(const PipelineArgs &a) { return (a.nblocks ? 3u : 0u) + (a.nframes ? 1u : 0u); }
+
+}  // namespace b200z
