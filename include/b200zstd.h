@@ -228,6 +228,11 @@ int b200z_batch_prepare(b200z_ctx *ctx, const uint8_t *input, size_t input_len, 
                         const b200z_dict *forced_dict, uint64_t max_window_size, b200z_batch **out);
 int b200z_batch_run(b200z_batch *b, uint8_t *d_output, size_t output_cap);
 int b200z_batch_finish(b200z_batch *b, b200z_frame_result *results);
+/* b200z_batch_run with a CUDA event between kernels: synchronises and returns each kernel's device milliseconds
+ * (stage_ms[i] for kernel b200z_stage_kernel_name(i), i < b200z_num_stages()).  Profiling aid for bench.py. */
+int b200z_batch_run_profile(b200z_batch *b, uint8_t *d_output, size_t output_cap, float *stage_ms, size_t nstages);
+int b200z_num_stages(void);
+const char *b200z_stage_kernel_name(int stage);
 /* facts about a prepared batch: [0] frames [1] blocks [2] compressed blocks [3] input bytes planned
  * [4] literal-scratch bytes [5] sequences [6] kernel launches per run */
 int b200z_batch_info(const b200z_batch *b, uint64_t out[8]);

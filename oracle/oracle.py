@@ -257,14 +257,15 @@ def decode_frame(data, dict_raw=None, raw_dict=None):
     return d.collect(), d
 
 
-def bulk_decode(inp, in_off, in_sz, out_off, out_cap, raw_dict=None, nthreads=1):
+def bulk_decode(inp, in_off, in_sz, out_off, out_cap, raw_dict=None, nthreads=1, out=None):
     """Decode many independent frames (numpy arrays of offsets/sizes); returns (output ndarray, sizes)."""
     L = lib()
     inp = np.ascontiguousarray(inp, dtype=np.uint8)
     in_off = np.ascontiguousarray(in_off, dtype=np.uint64); in_sz = np.ascontiguousarray(in_sz, dtype=np.uint64)
     out_off = np.ascontiguousarray(out_off, dtype=np.uint64); out_cap = np.ascontiguousarray(out_cap, dtype=np.uint64)
     total = int((out_off + out_cap).max()) if len(out_off) else 0
-    out = np.empty(total, dtype=np.uint8)
+    if out is None or len(out) < total:
+        out = np.empty(total, dtype=np.uint8)
     out_sz = np.zeros(len(in_off), dtype=np.uint64)
     e = L.zo_bulk_decode(inp.ctypes.data, in_off.ctypes.data, in_sz.ctypes.data, len(in_off), out.ctypes.data,
                          out_off.ctypes.data, out_cap.ctypes.data, out_sz.ctypes.data,

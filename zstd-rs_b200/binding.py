@@ -86,6 +86,9 @@ def lib():
         "b200z_batch_prepare": (C.c_int, [vp, vp, sz, C.c_int, vp, sz, pp, sz, vp, C.c_uint64, pp]),
         "b200z_batch_run": (C.c_int, [vp, vp, sz]),
         "b200z_batch_finish": (C.c_int, [vp, vp]),
+        "b200z_batch_run_profile": (C.c_int, [vp, vp, sz, C.POINTER(C.c_float), sz]),
+        "b200z_num_stages": (C.c_int, []),
+        "b200z_stage_kernel_name": (C.c_char_p, [C.c_int]),
         "b200z_batch_info": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
         "b200z_batch_debug_literals": (C.c_int, [vp, C.c_uint32, vp, sz, C.POINTER(sz)]),
         "b200z_batch_debug_sequences": (C.c_int, [vp, C.c_uint32, vp, sz, C.POINTER(sz)]),
@@ -296,6 +299,14 @@ class Batch:
         op, ol, _k = _ptr(d_output)
         assert _is_device(d_output), "Batch.run writes into device memory"
         self.ctx._chk(self.ctx.L.b200z_batch_run(self.h, op, ol))
+
+    def run_profile(self, d_output):
+        """{kernel name: device ms} for one pass, measured with CUDA events between the kernels."""
+        op, ol, _k = _ptr(d_output)
+        n = self.ctx.L.b200z_num_stages()
+        ms = (C.c_float * n)()
+        self.ctx._chk(self.ctx.L.b200z_batch_run_profile(self.h, op, ol, ms, n))
+        return {self.ctx.L.b200z_stage_kernel_name(i).decode(): float(ms[i]) for i in range(n)}
 
     def finish(self):
         res = np.zeros(len(self.frames), dtype=FRAME_RESULT_DTYPE)

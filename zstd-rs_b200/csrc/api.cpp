@@ -460,6 +460,33 @@ extern "C" int b200z_batch_run(b200z_batch *b, uint8_t *d_output, size_t output_
     return 0;
 }
 
+// Same as b200z_batch_run but with a CUDA event between stages; synchronises and reports per-kernel milliseconds.
+extern "C" int b200z_batch_run_profile(b200z_batch *b, uint8_t *d_output, size_t output_cap, float *stage_ms, size_t nstages) {
+    if (!b || !stage_ms) return B200Z_ERR_INVALID_ARGUMENT;
+    b200z_ctx *c = b->ctx;
+    if (int e = c->use()) return e;
+    Submission &s = b->sub;
+    if (!s.states.empty())
+        CU(c, cudaMemcpyAsync(s.d_states.p, b->d_states_init.p, s.states.size() * sizeof(FrameState), cudaMemcpyDeviceToDevice, c->stream));
+    PipelineArgs a = s.args(b->d_input, d_output, output_cap);
+    cudaEvent_t ev[kNumStages + 1];
+    for (auto &e : ev) CU(c, cudaEventCreate(&e));
+    CU(c, cudaEventRecord(ev[0], c->stream));
+    for (int st = 0; st < kNumStages; st++) {
+        int e = launch_stage(a, st, c->stream);
+        if (e) return c->set_cuda_err((cudaError_t)e, "launch_stage");
+        CU(c, cudaEventRecord(ev[st + 1], c->stream));
+    }
+    c->launches += pipeline_launch_count(a);
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (int st = 0; st < kNumStages && (size_t)st < nstages; st++) CU(c, cudaEventElapsedTime(&stage_ms[st], ev[st], ev[st + 1]));
+    for (auto &e : ev) cudaEventDestroy(e);
+    b->ran = true;
+    return 0;
+}
+extern "C" int b200z_num_stages(void) { return kNumStages; }
+extern "C" const char *b200z_stage_kernel_name(int stage) { return stage >= 0 && stage < kNumStages ? kStageNames[stage] : ""; }
+
 static void fill_result(const b200z_batch *b, size_t i, const FrameState *st, b200z_frame_result &r) {
     const FramePlanInfo &fi = b->info[i];
     memset(&r, 0, sizeof r);

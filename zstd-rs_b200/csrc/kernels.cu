@@ -443,16 +443,27 @@ int launch_predefined(FseSlot *predef, cudaStream_t s) {
     return (int)cudaGetLastError();
 }
 
-int launch_pipeline(const PipelineArgs &a, cudaStream_t s) {
-    if (a.nblocks) {
-        k_setup<<<cdiv(a.nblocks, 64), 64, 0, s>>>(a.descs, a.aux, a.input, a.nblocks);
-        k_huf<<<cdiv(a.nblocks * 4, 128), 128, 0, s>>>(a.descs, a.aux, a.input, a.lit_scratch, a.nblocks);
-        k_fse<<<cdiv(a.nblocks, 32), 32, 0, s>>>(a.descs, a.aux, a.input, a.seq_scratch, a.nblocks);
+const char *const kStageNames[kNumStages] = {"k_setup", "k_huf", "k_fse", "k_exec"};
+
+// one stage of the pipeline; a stage with nothing to do launches nothing and returns 0
+int launch_stage(const PipelineArgs &a, int stage, cudaStream_t s) {
+    switch (stage) {
+        case 0: if (a.nblocks) k_setup<<<cdiv(a.nblocks, 64), 64, 0, s>>>(a.descs, a.aux, a.input, a.nblocks); break;
+        case 1: if (a.nblocks) k_huf<<<cdiv(a.nblocks * 4, 128), 128, 0, s>>>(a.descs, a.aux, a.input, a.lit_scratch, a.nblocks); break;
+        case 2: if (a.nblocks) k_fse<<<cdiv(a.nblocks, 32), 32, 0, s>>>(a.descs, a.aux, a.input, a.seq_scratch, a.nblocks); break;
+        case 3:
+            if (a.nframes)
+                k_exec<<<cdiv(a.nframes * 32, 128), 128, 0, s>>>(a.descs, a.aux, a.frames, a.states, a.input, a.lit_scratch, a.seq_scratch,
+                                                                a.output, a.output_cap, a.nframes);
+            break;
+        default: break;
     }
-    if (a.nframes)
-        k_exec<<<cdiv(a.nframes * 32, 128), 128, 0, s>>>(a.descs, a.aux, a.frames, a.states, a.input, a.lit_scratch, a.seq_scratch,
-                                                        a.output, a.output_cap, a.nframes);
     return (int)cudaGetLastError();
+}
+
+int launch_pipeline(const PipelineArgs &a, cudaStream_t s) {
+    for (int st = 0; st < kNumStages; st++) { int e = launch_stage(a, st, s); if (e) return e; }
+    return 0;
 }
 
 uint32_t pipeline_launch_count(const PipelineArgs &a) { return (a.nblocks ? 3u : 0u) + (a.nframes ? 1u : 0u); }

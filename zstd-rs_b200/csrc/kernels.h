@@ -22,6 +22,9 @@ struct PipelineArgs {
 };
 
 int launch_predefined(FseSlot *predef, cudaStream_t s);
+constexpr int kNumStages = 4;
+extern const char *const kStageNames[kNumStages];
+int launch_stage(const PipelineArgs &a, int stage, cudaStream_t s);
 int launch_pipeline(const PipelineArgs &a, cudaStream_t s);
 uint32_t pipeline_launch_count(const PipelineArgs &a);
 
