@@ -4,7 +4,7 @@ libzstd plays two roles here, neither on the measured path:
   * GENERATOR of the compressed frames of every synthetic config (the reference's own interop contract is
     "decode what C zstd level 3 produced", ruzstd/fuzz/fuzz_targets/interop.rs:31-33,55-65);
   * secondary oracle in tests (ZSTD_decompress on the same frames).
-All randomness is numpy PCG64 with fixed seeds; datasets are cached under .cache/.
+All randomness is numpy PCG64 with fixed seeds; datasets are cached under $B200Z_CACHE (default /tmp/b200z_cache).
 """
 import ctypes as C
 import hashlib
@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 
 _ROOT = os.path.dirname(os.path.abspath(__file__))
-CACHE = os.environ.get("B200Z_CACHE", os.path.join(_ROOT, ".cache"))
+CACHE = os.environ.get("B200Z_CACHE", "/tmp/b200z_cache")
 
 ZSTD_c_compressionLevel, ZSTD_c_windowLog, ZSTD_c_contentSizeFlag, ZSTD_c_checksumFlag = 100, 101, 200, 201
 

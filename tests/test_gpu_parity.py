@@ -325,19 +325,24 @@ def test_synthetic_configs_small(pkg, ctx, oracle):
 
 
 def test_target_too_small_and_capacity_isolation(pkg, ctx):
-    """A frame that does not fit its out_cap fails alone and never writes past its slot."""
+    """A frame that does not fit its out_cap fails alone and never writes past its slot (checked on the device buffer)."""
+    import torch
     import datagen as G
     fs = G.config_c3(nframes=4, cache=False)
     io = fs.frames_io()
     io["out_cap"][2] = 1000
-    out = np.full(fs.D + 16, 0xAB, dtype=np.uint8)
-    res = pkg.decode_frames(ctx, fs.comp, io, out)
+    d_out = torch.full((fs.D + 64,), 0xAB, dtype=torch.uint8, device="cuda")
+    b = pkg.Batch(ctx, fs.comp, io)
+    b.run(d_out)
+    res = b.finish()
+    out = d_out.cpu().numpy()
     names = pkg.error_names()
     assert names[int(res[2]["status"])] == "B200Z_ERR_TARGET_TOO_SMALL"
     for i in (0, 1, 3):
         assert res[i]["status"] == 0
         assert np.array_equal(out[fs.out_off[i]:fs.out_off[i] + fs.out_size[i]], fs.plain[fs.out_off[i]:fs.out_off[i] + fs.out_size[i]])
     assert (out[int(fs.out_off[2]) + 1000:int(fs.out_off[3])] == 0xAB).all()
+    assert (out[fs.D:] == 0xAB).all()
 
 
 def test_truncation_sweep_matches_oracle(pkg, ctx, oracle):
