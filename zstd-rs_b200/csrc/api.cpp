@@ -109,6 +109,7 @@ extern "C" int b200z_ctx_create(int device, b200z_ctx **out) {
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return B200Z_ERR_NO_DEVICE; }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return B200Z_ERR_NO_DEVICE; }
     if (cudaMalloc((void **)&c->d_predef, sizeof(FseSlot)) != cudaSuccess) { cudaGetLastError(); return B200Z_ERR_OUT_OF_MEMORY; }
+    if (init_kernels()) { cudaGetLastError(); return B200Z_ERR_CUDA; }
     int e = launch_predefined(c->d_predef, c->stream);
     if (e || cudaStreamSynchronize(c->stream) != cudaSuccess) { cudaGetLastError(); return B200Z_ERR_CUDA; }
     c->launches = 1;

@@ -23,26 +23,41 @@ constexpr uint32_t HUF_MAX_BITS = 11;         // huff0_decoder.rs:9
 constexpr uint32_t HUF_TABLE_ENTRIES = 2048;  // 1 << 11
 constexpr uint32_t FSE_MAX_ENTRIES = 512;     // LL/ML max log 9 (sequence_section_decoder.rs:288-292)
 
-// huff0 LUT: entry = symbol | num_bits << 8   (huff0_decoder.rs:389-394 Entry{symbol,num_bits})
+// huff0 LUT, split so that it costs 3 KiB of shared memory per block instead of 4 (occupancy: every block of a
+// 1 GiB submission is in flight at once): sym[i] = symbol, nb4[i >> 1] holds the 4-bit code length of entries
+// 2k (low nibble) and 2k+1 (high nibble).   (huff0_decoder.rs:389-394 Entry{symbol,num_bits})
 struct alignas(16) HufSlot {
     uint32_t max_bits;  // 0 = uninitialised (literals_section_decoder.rs:61-63)
     uint32_t status;    // build error (b200z_error) or 0
     uint32_t pad[2];
-    uint16_t e[HUF_TABLE_ENTRIES];
+    uint8_t sym[HUF_TABLE_ENTRIES];
+    uint8_t nb4[HUF_TABLE_ENTRIES / 2];
 };
+__host__ __device__ inline void huf_set(HufSlot *s, uint32_t i, uint32_t symbol, uint32_t nb) {
+    s->sym[i] = (uint8_t)symbol;
+    uint8_t o = s->nb4[i >> 1];
+    s->nb4[i >> 1] = (i & 1u) ? (uint8_t)((o & 0x0Fu) | (nb << 4)) : (uint8_t)((o & 0xF0u) | nb);
+}
+__host__ __device__ inline uint32_t huf_nb(const uint8_t *nb4, uint32_t i) { return (nb4[i >> 1] >> ((i & 1u) * 4u)) & 15u; }
 
-// FSE LUT: entry = base_line | num_bits << 16 | symbol << 24   (fse_decoder.rs:312-320 Entry)
-// An RLE mode is stored as log = 0, e[0] = {0, 0, symbol}: reading 0 bits always lands on entry 0, which is
+// FSE LUT, 16 bits per state so that LL + ML + OF of one block cost 2.5 KiB of shared memory:
+//   entry = f | symbol << 10,   f = (1 << (log - num_bits)) | (base_line >> num_bits)
+// base_line is always a multiple of 2^num_bits (fse_decoder.rs:340-366: baselines are whole slices), so
+//   num_bits = log - floor(log2 f),  base_line = (f - 2^floor(log2 f)) << num_bits     (fse_decoder.rs:312-320 Entry)
+// An RLE mode is stored as log = 0, e[0] = {f = 1, symbol}: reading 0 bits always lands on entry 0, which is
 // what decode_sequences_with_rle does by substituting the constant code (sequence_section_decoder.rs:74-88).
 struct alignas(16) FseTab {
     uint32_t log;     // accuracy_log, 0 for RLE
     uint32_t valid;   // 0 = never built (FSEDecoderError::TableIsUninitialized, fse_decoder.rs:33-35)
     uint32_t is_rle;
     uint32_t pad;
-    uint32_t e[FSE_MAX_ENTRIES];
+    uint16_t e[FSE_MAX_ENTRIES];
 };
 struct alignas(16) FseSlot { FseTab ll, of, ml; };
 
+__host__ __device__ inline uint16_t fse_pack16(uint32_t log, uint32_t base, uint32_t nb, uint32_t sym) {
+    return (uint16_t)(((1u << (log - nb)) | (base >> nb)) | (sym << 10));
+}
 __host__ __device__ inline uint32_t fse_pack(uint32_t base, uint32_t nb, uint32_t sym) { return base | (nb << 16) | (sym << 24); }
 
 // One descriptor per block; everything the reference derives in decompress_block before calling the three hot

@@ -16,7 +16,7 @@
 #include <stdint.h>
 
 #include "kernels.h"
-#include "tables.cuh"
+#include "setup.cuh"
 
 namespace b200z {
 
@@ -85,110 +85,242 @@ __global__ void k_predefined(FseSlot *predef) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_setup: one thread per block.
+// k_setup: one WARP per block.  Lane 0 walks the bit-serial descriptions; the table expansion is warp-parallel
+// out of shared memory (setup.cuh).  Tables land in global slots (3 KiB huff0 / 3 x 1 KiB FSE) that the decode
+// kernels stage into shared memory.
 // ------------------------------------------------------------------------------------------------------------
-__device__ int setup_one_seq_table(uint32_t mode, const uint8_t *&p, uint32_t &rem, uint32_t max_log, uint32_t max_sym,
-                                   FseTab *tab, int missing_err) {
+constexpr int SETUP_WARPS = 4;
+
+__device__ int setup_seq_table_warp(SetupScratch &sc, uint32_t mode, const uint8_t *&p, uint32_t &rem, uint32_t max_log, uint32_t max_sym,
+                                    FseTab *tab, int missing_err) {
+    const uint32_t lane = lane_id();
     if (mode == MODE_FSE) {
-        uint32_t used = 0;
-        int e = fse_build_decoder(p, rem, max_log, max_sym, tab, used);
+        uint32_t used = 0, nprobs = 0, log = 0;
+        int e = 0;
+        if (lane == 0) e = fse_read_probabilities(p, rem, max_log, max_sym, sc.probs, nprobs, log, used);
+        e = __shfl_sync(0xffffffffu, e, 0);
         if (e) return e;
-        p += used; rem -= used;  // used <= rem: the forward reader never reads past the slice
+        used = __shfl_sync(0xffffffffu, used, 0); nprobs = __shfl_sync(0xffffffffu, nprobs, 0); log = __shfl_sync(0xffffffffu, log, 0);
+        __syncwarp();
+        e = fse_build_warp(sc, nprobs, log, max_sym, tab);
+        if (e) return e;
+        p += used; rem -= used;
     } else if (mode == MODE_RLE) {
         if (rem == 0) return missing_err;
         uint32_t sym = p[0];
         if (sym > max_sym) return B200Z_ERR_SEQ_MISSING_BYTE_FOR_RLE_ML_TABLE;  // sic, sequence_section_decoder.rs:321,356,391
-        tab->log = 0; tab->valid = 1; tab->is_rle = 1; tab->e[0] = fse_pack(0, 0, sym);
+        if (lane == 0) { tab->log = 0; tab->valid = 1; tab->is_rle = 1; tab->e[0] = fse_pack16(0, 0, 0, sym); }
         p += 1; rem -= 1;
     }
     return 0;
 }
 
-__global__ void k_setup(const BlockDesc *__restrict__ descs, BlockAux *__restrict__ aux, const uint8_t *__restrict__ input, uint32_t nblocks) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(const BlockDesc *__restrict__ descs, BlockAux *__restrict__ aux,
+                                                          const uint8_t *__restrict__ input, uint32_t nblocks) {
+    __shared__ SetupScratch scratch[SETUP_WARPS];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t b = blockIdx.x * SETUP_WARPS + warp;
     if (b >= nblocks) return;
+    SetupScratch &sc = scratch[warp];
     const BlockDesc &d = descs[b];
-    BlockAux a;
-    a.status = 0; a.out_size = 0; a.lit_streams_off = 0; a.seq_bits_off = 0; a.out_off = 0; a.sum_ll = 0; a.pad = 0;
-    uint32_t st_lit = 0, st_seq = 0;
+    uint32_t st_lit = 0, st_seq = 0, lit_streams_off = 0, seq_bits_off = 0;
     if (d.btype == BT_COMPRESSED && !(d.host_status && (d.host_status >> 24) == 1)) {
         const uint8_t *content = input + d.src_off;
         if (d.lit_type == LT_COMPRESSED) {
-            uint32_t used = 0;
-            int e = huf_build_decoder(content + d.lit_off, d.lit_comp_size, d.huf_build, used);
-            if (e) st_lit = mk_status((uint32_t)e, B200Z_STAGE_LITERALS);
-            a.lit_streams_off = used;
+            uint32_t used = 0, nweights = 0;
+            int e = 0;
+            if (lane == 0) e = huf_read_weights(content + d.lit_off, d.lit_comp_size, sc.weights, nweights, used);
+            e = __shfl_sync(0xffffffffu, e, 0);
+            used = __shfl_sync(0xffffffffu, used, 0); nweights = __shfl_sync(0xffffffffu, nweights, 0);
+            __syncwarp();
+            if (!e) e = huf_build_warp(sc, nweights, d.huf_build);
+            if (e) { st_lit = mk_status((uint32_t)e, B200Z_STAGE_LITERALS); if (lane == 0) { d.huf_build->max_bits = 0; d.huf_build->status = (uint32_t)e; } }
+            lit_streams_off = used;
         } else if (d.lit_type == LT_TREELESS) {
             if (d.huf == nullptr) st_lit = mk_status(B200Z_ERR_LIT_UNINITIALIZED_HUFFMAN_TABLE, B200Z_STAGE_LITERALS);
         }
         if (d.nseq != 0 && !d.host_status) {
             const uint8_t *p = content + d.seq_off;
             uint32_t rem = d.src_size - d.seq_off;
-            int e = setup_one_seq_table(d.modes >> 6, p, rem, 9, 35, d.fse_build ? &d.fse_build->ll : nullptr, B200Z_ERR_SEQ_MISSING_BYTE_FOR_RLE_LL_TABLE);
-            if (!e) e = setup_one_seq_table((d.modes >> 4) & 3, p, rem, 8, 31, d.fse_build ? &d.fse_build->of : nullptr, B200Z_ERR_SEQ_MISSING_BYTE_FOR_RLE_OF_TABLE);
-            if (!e) e = setup_one_seq_table((d.modes >> 2) & 3, p, rem, 9, 52, d.fse_build ? &d.fse_build->ml : nullptr, B200Z_ERR_SEQ_MISSING_BYTE_FOR_RLE_ML_TABLE);
+            int e = setup_seq_table_warp(sc, d.modes >> 6, p, rem, 9, 35, d.fse_build ? &d.fse_build->ll : nullptr, B200Z_ERR_SEQ_MISSING_BYTE_FOR_RLE_LL_TABLE);
+            __syncwarp();
+            if (!e) e = setup_seq_table_warp(sc, (d.modes >> 4) & 3, p, rem, 8, 31, d.fse_build ? &d.fse_build->of : nullptr, B200Z_ERR_SEQ_MISSING_BYTE_FOR_RLE_OF_TABLE);
+            __syncwarp();
+            if (!e) e = setup_seq_table_warp(sc, (d.modes >> 2) & 3, p, rem, 9, 52, d.fse_build ? &d.fse_build->ml : nullptr, B200Z_ERR_SEQ_MISSING_BYTE_FOR_RLE_ML_TABLE);
             if (e) st_seq = mk_status((uint32_t)e, B200Z_STAGE_SEQUENCES);
-            a.seq_bits_off = (uint32_t)(p - content);
+            seq_bits_off = (uint32_t)(p - content);
         }
     }
-    a.status = st_lit;   // literals-stage status; sequence-stage status kept separately in `pad` until k_fse merges
-    a.pad = st_seq;
-    aux[b] = a;
+    if (lane == 0) {
+        BlockAux a;
+        a.status = st_lit;   // literals-stage status; the sequence-stage status travels in `pad` until k_exec orders them
+        a.out_size = 0; a.lit_streams_off = lit_streams_off; a.seq_bits_off = seq_bits_off; a.out_off = 0; a.sum_ll = 0; a.pad = st_seq;
+        aux[b] = a;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_huf: literals.
+// k_huf: literals.  One CTA (one warp) = 8 blocks x 4 streams; the 8 huff0 LUTs (3 KiB each, split symbol /
+// 4-bit length) are staged into shared memory; every lane walks its own reversed bitstream with a 64-bit window
+// refilled by aligned 32-bit words (next word prefetched one refill ahead) and writes its symbols in 16-byte
+// vectors.
 // ------------------------------------------------------------------------------------------------------------
-// Decode one huff0 stream: symbols are emitted while the bits consumed by emitted symbols are < the stream's
-// data bits (literals_section_decoder.rs:112-115: `while bits_remaining > -max_num_bits`), at most `cap`.
-// Returns: 0 = stream exhausted exactly, 1 = exhausted but over-read (BitstreamReadMismatch for 4 streams),
-// 2 = cap reached before exhaustion, 3 = ExtraPadding.
-__device__ __forceinline__ int huf_stream(const uint16_t *__restrict__ tab, uint32_t mb, const uint8_t *src, uint32_t len,
-                                          uint8_t *dst, uint32_t store_limit, uint32_t cap, uint32_t &count) {
-    RevBits br;
+constexpr uint32_t HUF_BLOCKS_PER_CTA = 8;
+constexpr uint32_t HUF_SMEM_PER_BLOCK = HUF_TABLE_ENTRIES + HUF_TABLE_ENTRIES / 2;  // 3072
+
+struct HufBits {
+    const uint32_t *base;
+    uint32_t hi, lo;   // unread bits, left aligned in hi:lo
+    int32_t fill;
+    int32_t wi;
+    uint32_t g0;
+    uint32_t nextw;    // word wi-1, already loaded
+    int32_t p;
+    __device__ __forceinline__ uint32_t fetch(int32_t i) const {
+        uint32_t w = 0;
+        if (i >= 0) { w = __ldg(base + i); if (i == 0) w &= ~((1u << g0) - 1u); }
+        return w;
+    }
+    __device__ __forceinline__ bool init(const uint8_t *src, uint32_t len) {
+        if (len == 0) return false;
+        uint32_t last = src[len - 1];
+        if (last == 0) return false;
+        uintptr_t a = (uintptr_t)src;
+        base = (const uint32_t *)(a & ~(uintptr_t)3);
+        g0 = (uint32_t)(a & 3) * 8u;
+        p = (int32_t)((len - 1) * 8u + (31u - (uint32_t)__clz((int)last)));
+        hi = lo = 0; fill = 0; wi = 0;
+        if (p > 0) {
+            uint32_t gtop = g0 + (uint32_t)p - 1u;
+            wi = (int32_t)(gtop >> 5);
+            uint32_t w = fetch(wi);
+            uint32_t used = (gtop & 31u) + 1u;
+            hi = w << (32u - used);
+            fill = (int32_t)used;
+        }
+        nextw = fetch(wi - 1);
+        return true;
+    }
+    // afterwards fill > 32: at least 32 real-or-virtual bits ready
+    __device__ __forceinline__ void refill() {
+        if (fill <= 32) {
+            uint32_t w = nextw;
+            --wi;
+            nextw = fetch(wi - 1);
+            // append w below the `fill` valid bits of hi:lo
+            if (fill == 32) lo = w;
+            else if (fill == 0) hi = w;
+            else { hi |= w >> fill; lo = w << (32 - fill); }   // fill in [1, 31]
+            fill += 32;
+        }
+    }
+    __device__ __forceinline__ void skip(uint32_t n) {  // n <= 31
+        hi = __funnelshift_l(lo, hi, n);
+        lo <<= n;
+        fill -= (int32_t)n;
+        p -= (int32_t)n;
+    }
+};
+
+// returns 0 exhausted exactly, 1 over-read, 2 cap reached, 3 ExtraPadding
+__device__ __forceinline__ int huf_stream2(const uint8_t *__restrict__ tsym, const uint8_t *__restrict__ tnb, uint32_t mb,
+                                           const uint8_t *src, uint32_t len, uint8_t *dst, uint32_t store_limit, uint32_t cap, uint32_t &count) {
+    HufBits br;
     count = 0;
     if (!br.init(src, len)) return 3;
     uint32_t n = 0;
+    const uint32_t sh = 32u - mb;
+    // scalar head until dst + n is 16-byte aligned
+    while (br.p > 0 && n < cap && (((uintptr_t)(dst + n)) & 15u)) {
+        br.refill();
+        uint32_t idx = br.hi >> sh;
+        if (n < store_limit) dst[n] = tsym[idx];
+        n++;
+        br.skip((tnb[idx >> 1] >> ((idx & 1u) * 4u)) & 15u);
+    }
+    // vector body: 16 symbols per store while at least 16 full-length codes remain
+    while (br.p >= (int32_t)(16 * HUF_MAX_BITS) && n + 16 <= cap && n + 16 <= store_limit) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k += 2) {
+                br.refill();   // > 32 bits: two codes of <= 11 bits
+                uint32_t i0 = br.hi >> sh;
+                uint32_t s0 = tsym[i0];
+                br.skip((tnb[i0 >> 1] >> ((i0 & 1u) * 4u)) & 15u);
+                uint32_t i1 = br.hi >> sh;
+                uint32_t s1 = tsym[i1];
+                br.skip((tnb[i1 >> 1] >> ((i1 & 1u) * 4u)) & 15u);
+                acc |= (s0 << (8 * k)) | (s1 << (8 * k + 8));
+            }
+            w[q] = acc;
+        }
+        *reinterpret_cast<uint4 *>(dst + n) = make_uint4(w[0], w[1], w[2], w[3]);
+        n += 16;
+    }
+    // scalar tail
     while (br.p > 0) {
         if (n == cap) { count = n; return 2; }
         br.refill();
-        uint32_t e = tab[br.peek(mb)];
-        if (n < store_limit) dst[n] = (uint8_t)e;
+        uint32_t idx = br.hi >> sh;
+        if (n < store_limit) dst[n] = tsym[idx];
         n++;
-        br.get(e >> 8);
+        br.skip((tnb[idx >> 1] >> ((idx & 1u) * 4u)) & 15u);
     }
     count = n;
     return br.p == 0 ? 0 : 1;
 }
 
-__global__ void k_huf(const BlockDesc *__restrict__ descs, BlockAux *__restrict__ aux, const uint8_t *__restrict__ input,
-                      uint8_t *__restrict__ lit_scratch, uint32_t nblocks) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t b = t >> 2, k = t & 3;
+__global__ void __launch_bounds__(32) k_huf(const BlockDesc *__restrict__ descs, BlockAux *__restrict__ aux, const uint8_t *__restrict__ input,
+                                          uint8_t *__restrict__ lit_scratch, uint32_t nblocks) {
+    extern __shared__ __align__(16) uint8_t smem_huf[];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t b0 = blockIdx.x * HUF_BLOCKS_PER_CTA;
+    const uint32_t g = lane >> 2, k = lane & 3;
+    const uint32_t b = b0 + g;
     bool active = b < nblocks;
-    uint32_t err = 0;
-    bool work = false;
     const BlockDesc *d = nullptr;
+    bool work = false;
+    uint32_t err = 0;
+    const HufSlot *slot = nullptr;
     if (active) {
         d = &descs[b];
         work = d->btype == BT_COMPRESSED && (d->lit_type == LT_COMPRESSED || d->lit_type == LT_TREELESS) &&
                !(d->host_status && (d->host_status >> 24) == 1) && aux[b].status == 0;
+        if (work) {
+            slot = d->huf;
+            if (slot == nullptr || slot->max_bits == 0) { err = B200Z_ERR_LIT_UNINITIALIZED_HUFFMAN_TABLE; work = false; }
+        }
     }
-    // all four lanes of a group take the same branches up to the per-stream decode
+    // ---- stage the LUTs: group j's table is copied by the whole warp, 16 bytes per lane per step
+    for (uint32_t j = 0; j < HUF_BLOCKS_PER_CTA; j++) {
+        unsigned long long sp = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)(work ? slot : nullptr), j * 4);
+        if (!sp) continue;
+        const HufSlot *s = (const HufSlot *)(uintptr_t)sp;
+        uint32_t mbj = s->max_bits;
+        uint32_t n_sym16 = ((1u << mbj) + 15) >> 4, n_nb16 = (((1u << mbj) >> 1) + 15) >> 4;
+        uint4 *dsym = reinterpret_cast<uint4 *>(smem_huf + j * HUF_SMEM_PER_BLOCK);
+        uint4 *dnb = reinterpret_cast<uint4 *>(smem_huf + j * HUF_SMEM_PER_BLOCK + HUF_TABLE_ENTRIES);
+        const uint4 *ssym = reinterpret_cast<const uint4 *>(s->sym);
+        const uint4 *snb = reinterpret_cast<const uint4 *>(s->nb4);
+        for (uint32_t i = lane; i < n_sym16; i += 32) dsym[i] = ssym[i];
+        for (uint32_t i = lane; i < n_nb16; i += 32) dnb[i] = snb[i];
+    }
+    __syncwarp();
+    const uint8_t *tsym = smem_huf + g * HUF_SMEM_PER_BLOCK;
+    const uint8_t *tnb = tsym + HUF_TABLE_ENTRIES;
+
     int rc = 0; uint32_t count = 0; bool irregular = false;
-    const uint8_t *payload = nullptr; uint32_t plen = 0; const HufSlot *slot = nullptr; uint8_t *dst = nullptr;
-    uint32_t j1 = 0, j2 = 0, j3 = 0;
     if (work) {
-        slot = d->huf;
         uint32_t so = aux[b].lit_streams_off;
-        payload = input + d->src_off + d->lit_off + so;
-        plen = d->lit_comp_size - so;
-        dst = lit_scratch + d->lit_buf_off;
-        if (slot == nullptr || slot->max_bits == 0) { err = B200Z_ERR_LIT_UNINITIALIZED_HUFFMAN_TABLE; work = false; }
-    }
-    if (work) {
+        const uint8_t *payload = input + d->src_off + d->lit_off + so;
+        uint32_t plen = d->lit_comp_size - so;
+        uint8_t *dst = lit_scratch + d->lit_buf_off;
         uint32_t mb = slot->max_bits, regen = d->regen_size;
         if (d->nstreams == 4) {
+            uint32_t j1 = 0, j2 = 0, j3 = 0;
             if (plen < 6) { err = B200Z_ERR_LIT_MISSING_BYTES_FOR_JUMP_HEADER; }
             else {
                 j1 = payload[0] | (payload[1] << 8); j2 = j1 + (payload[2] | (payload[3] << 8)); j3 = j2 + (payload[4] | (payload[5] << 8));
@@ -197,23 +329,22 @@ __global__ void k_huf(const BlockDesc *__restrict__ descs, BlockAux *__restrict_
             if (!err) {
                 const uint8_t *s0 = payload + 6;
                 uint32_t S = (regen + 3) >> 2;
+                uint32_t off[5] = {0, j1, j2, j3, plen - 6};
                 // fast path: the standard split -- streams 0..2 regenerate S bytes, stream 3 the rest
                 if (regen >= 3 * S) {
-                    uint32_t off[5] = {0, j1, j2, j3, plen - 6};
                     uint32_t cap = k < 3 ? S : regen - 3 * S;
-                    rc = huf_stream(slot->e, mb, s0 + off[k], off[k + 1] - off[k], dst + k * S, cap, cap, count);
+                    rc = huf_stream2(tsym, tnb, mb, s0 + off[k], off[k + 1] - off[k], dst + k * S, cap, cap, count);
                     irregular = (rc != 0) || (count != cap);
                 } else irregular = true;
-                // any anomaly in the group -> lane 0 replays the block with the reference's exact semantics
-                uint32_t gmask = 0xFu << (threadIdx.x & 28u & 31u);
+                // any anomaly in the group -> lane 0 of the group replays the block with the reference's exact semantics
+                uint32_t gmask = 0xFu << (lane & 28u);
                 bool any = __any_sync(gmask, irregular);
                 if (any && k == 0) {
-                    uint32_t off[5] = {0, j1, j2, j3, plen - 6};
                     uint32_t total = 0;
                     for (uint32_t s = 0; s < 4 && !err; s++) {
                         uint32_t c = 0;
                         uint32_t lim = total < regen ? regen - total : 0;
-                        int r = huf_stream(slot->e, mb, s0 + off[s], off[s + 1] - off[s], dst + (total < regen ? total : regen), lim, 0xFFFFFFFFu, c);
+                        int r = huf_stream2(tsym, tnb, mb, s0 + off[s], off[s + 1] - off[s], dst + (total < regen ? total : regen), lim, 0xFFFFFFFFu, c);
                         if (r == 3) err = B200Z_ERR_LIT_EXTRA_PADDING;
                         else if (r == 1) err = B200Z_ERR_LIT_BITSTREAM_READ_MISMATCH;
                         total += c;
@@ -223,7 +354,7 @@ __global__ void k_huf(const BlockDesc *__restrict__ descs, BlockAux *__restrict_
             }
         } else if (k == 0) {
             // single stream: no exact-landing check (literals_section_decoder.rs:143-147), only the total count
-            rc = huf_stream(slot->e, mb, payload, plen, dst, regen, 0xFFFFFFFFu, count);
+            rc = huf_stream2(tsym, tnb, mb, payload, plen, dst, regen, 0xFFFFFFFFu, count);
             if (rc == 3) err = B200Z_ERR_LIT_EXTRA_PADDING;
             else if (count != regen) err = B200Z_ERR_LIT_DECODED_LITERAL_COUNT_MISMATCH;
         }
@@ -232,55 +363,118 @@ __global__ void k_huf(const BlockDesc *__restrict__ descs, BlockAux *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_fse: sequences.  One lane per block.
+// k_fse: sequences.  One lane per block, one warp (32 blocks) per CTA; the 32 x (LL + ML + OF) 16-bit LUTs are
+// staged into shared memory (80 KiB), code -> (baseline, extra bits) comes from two small shared LUTs, the
+// reversed bitstream is read through a 64-bit window with the next aligned word prefetched, and sequences are
+// written four at a time as three 16-byte vectors.
 // ------------------------------------------------------------------------------------------------------------
+constexpr uint32_t FSE_BLOCKS_PER_CTA = 32;
+constexpr uint32_t FSE_TAB_U16 = 512 + 512 + 256;   // LL, ML, OF entries per block
+
 __constant__ uint32_t c_ll_base[36] = {0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,18,20,22,24,28,32,40,48,64,128,256,512,1024,2048,4096,8192,16384,32768,65536};
 __constant__ uint8_t c_ll_bits[36] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,6,7,8,9,10,11,12,13,14,15,16};
 __constant__ uint32_t c_ml_base[53] = {3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,30,31,32,33,34,35,37,39,41,43,47,51,59,67,83,99,131,259,515,1027,2051,4099,8195,16387,32771,65539};
 __constant__ uint8_t c_ml_bits[53] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,4,5,7,8,9,10,11,12,13,14,15,16};
 
-__global__ void k_fse(const BlockDesc *__restrict__ descs, BlockAux *__restrict__ aux, const uint8_t *__restrict__ input,
-                      uint32_t *__restrict__ seq_scratch, uint32_t nblocks) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nblocks) return;
-    const BlockDesc &d = descs[b];
-    uint32_t st_seq = aux[b].pad;
-    aux[b].pad = 0;
-    if (d.btype != BT_COMPRESSED) { aux[b].out_size = d.raw_size; return; }
-    if (d.host_status) return;
-    if (d.nseq == 0) { aux[b].out_size = d.regen_size; return; }
+struct FseState {
+    uint32_t e;   // current 16-bit entry
+    __device__ __forceinline__ uint32_t sym() const { return e >> 10; }
+    // num_bits and base_line out of the compact entry (b200z_types.h)
+    __device__ __forceinline__ void decode(uint32_t log, uint32_t &nb, uint32_t &base) const {
+        uint32_t f = e & 1023u;
+        uint32_t h = 31u - (uint32_t)__clz((int)f);
+        nb = log - h;
+        base = (f ^ (1u << h)) << nb;
+    }
+};
+
+__global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs, BlockAux *__restrict__ aux, const uint8_t *__restrict__ input,
+                                          uint32_t *__restrict__ seq_scratch, uint32_t nblocks) {
+    extern __shared__ __align__(16) uint8_t smem_fse[];
+    uint16_t *tabs = reinterpret_cast<uint16_t *>(smem_fse);
+    uint32_t *s_ll_base = reinterpret_cast<uint32_t *>(smem_fse + FSE_BLOCKS_PER_CTA * FSE_TAB_U16 * 2);
+    uint32_t *s_ml_base = s_ll_base + 36;
+    uint8_t *s_ll_bits = reinterpret_cast<uint8_t *>(s_ml_base + 53);
+    uint8_t *s_ml_bits = s_ll_bits + 36;
+    const uint32_t lane = threadIdx.x;
+    const uint32_t b = blockIdx.x * FSE_BLOCKS_PER_CTA + lane;
+    for (uint32_t i = lane; i < 36; i += 32) { s_ll_base[i] = c_ll_base[i]; s_ll_bits[i] = c_ll_bits[i]; }
+    for (uint32_t i = lane; i < 53; i += 32) { s_ml_base[i] = c_ml_base[i]; s_ml_bits[i] = c_ml_bits[i]; }
+
+    const bool active = b < nblocks;
+    const BlockDesc *d = active ? &descs[b] : nullptr;
+    uint32_t st_seq = 0;
+    bool run = false;
+    if (active) {
+        st_seq = aux[b].pad;
+        if (d->btype != BT_COMPRESSED) aux[b].out_size = d->raw_size;
+        else if (!d->host_status && d->nseq == 0) aux[b].out_size = d->regen_size;
+        run = d->btype == BT_COMPRESSED && !d->host_status && d->nseq != 0 && st_seq == 0;
+    }
+    const FseTab *tl = run ? d->ll : nullptr, *to = run ? d->of : nullptr, *tm = run ? d->ml : nullptr;
+    // ---- stage the tables of the 32 blocks (warp-cooperative, 16-byte vectors)
+    for (uint32_t j = 0; j < FSE_BLOCKS_PER_CTA; j++) {
+        const FseTab *pj[3];
+        pj[0] = (const FseTab *)(uintptr_t)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)tl, j);
+        pj[1] = (const FseTab *)(uintptr_t)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)tm, j);
+        pj[2] = (const FseTab *)(uintptr_t)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)to, j);
+        uint16_t *dstj = tabs + j * FSE_TAB_U16;
+        const uint32_t offs[3] = {0, 512, 1024};
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            if (!pj[t] || !pj[t]->valid) continue;
+            uint32_t n16 = ((2u << pj[t]->log) + 15) >> 4;   // bytes / 16
+            if (t == 2 && n16 > 32) n16 = 32;
+            if (n16 > 64) n16 = 64;
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(pj[t]->e);
+            uint4 *d4 = reinterpret_cast<uint4 *>(dstj + offs[t]);
+            for (uint32_t i = lane; i < n16; i += 32) d4[i] = s4[i];
+        }
+    }
+    __syncwarp();
+    if (!active) return;
+    if (!run) { aux[b].pad = st_seq; return; }
+
     uint32_t err = 0;
     uint64_t sum_ml = 0, sum_ll = 0;
-    if (st_seq == 0) {
-        const uint8_t *src = input + d.src_off + aux[b].seq_bits_off;
-        uint32_t len = d.src_size - aux[b].seq_bits_off;
-        RevBits br;
-        const FseTab *tl = d.ll, *to = d.of, *tm = d.ml;
-        uint32_t sl = 0, so = 0, sm = 0;
+    {
+        const uint8_t *src = input + d->src_off + aux[b].seq_bits_off;
+        uint32_t len = d->src_size - aux[b].seq_bits_off;
+        const uint16_t *TL = tabs + lane * FSE_TAB_U16, *TM = TL + 512, *TO = TL + 1024;
+        HufBits br;
+        FseState sl{0}, so{0}, sm{0};
+        uint32_t logL = 0, logM = 0, logO = 0;
         if (!br.init(src, len)) err = B200Z_ERR_SEQ_EXTRA_PADDING;
         // init order LL, OF, ML (sequence_section_decoder.rs:164-166); an RLE'd component reads 0 bits
-        if (!err) { if (!tl || !tl->valid) err = B200Z_ERR_FSE_TABLE_IS_UNINITIALIZED; else { br.refill(); sl = tl->e[br.get(tl->log)]; } }
-        if (!err) { if (!to || !to->valid) err = B200Z_ERR_FSE_TABLE_IS_UNINITIALIZED; else { br.refill(); so = to->e[br.get(to->log)]; } }
-        if (!err) { if (!tm || !tm->valid) err = B200Z_ERR_FSE_TABLE_IS_UNINITIALIZED; else { br.refill(); sm = tm->e[br.get(tm->log)]; } }
-        uint32_t *out = seq_scratch + d.seq_buf_off * 3;
-        const uint32_t nseq = d.nseq;
+        if (!err) { if (!tl || !tl->valid) err = B200Z_ERR_FSE_TABLE_IS_UNINITIALIZED; else { logL = tl->log; br.refill(); uint32_t i = logL ? br.hi >> (32u - logL) : 0u; br.skip(logL); sl.e = TL[i]; } }
+        if (!err) { if (!to || !to->valid) err = B200Z_ERR_FSE_TABLE_IS_UNINITIALIZED; else { logO = to->log; br.refill(); uint32_t i = logO ? br.hi >> (32u - logO) : 0u; br.skip(logO); so.e = TO[i]; } }
+        if (!err) { if (!tm || !tm->valid) err = B200Z_ERR_FSE_TABLE_IS_UNINITIALIZED; else { logM = tm->log; br.refill(); uint32_t i = logM ? br.hi >> (32u - logM) : 0u; br.skip(logM); sm.e = TM[i]; } }
+        uint32_t *out = seq_scratch + d->seq_buf_off * 3;
+        const uint32_t nseq = d->nseq;
         for (uint32_t i = 0; i < nseq && !err; i++) {
-            uint32_t ll_code = sl >> 24, ml_code = sm >> 24, of_code = so >> 24;
+            const uint32_t ll_code = sl.sym(), ml_code = sm.sym(), of_code = so.sym();
             if (ll_code > 35 || ml_code > 52) { err = B200Z_ERR_REFERENCE_WOULD_PANIC; break; }  // unreachable!: tables cap the symbols
             if (of_code > 31) { err = B200Z_ERR_SEQ_UNSUPPORTED_OFFSET; break; }
-            uint32_t ll_bits = c_ll_bits[ll_code], ml_bits = c_ml_bits[ml_code];
-            // extra bits in the order OF, ML, LL (get_bits_triple, :185)
-            br.refill(); uint32_t obits = br.get(of_code);
-            br.refill(); uint32_t ml_add = br.get(ml_bits); uint32_t ll_add = br.get(ll_bits);
-            uint32_t offset = obits + (1u << of_code);
-            uint32_t ll = c_ll_base[ll_code] + ll_add, ml = c_ml_base[ml_code] + ml_add;
+            const uint32_t ll_bits = s_ll_bits[ll_code], ml_bits = s_ml_bits[ml_code];
+            uint32_t nbL, nbM, nbO, baseL, baseM, baseO;
+            sl.decode(logL, nbL, baseL); sm.decode(logM, nbM, baseM); so.decode(logO, nbO, baseO);
+            // extra bits in the order OF, ML, LL (get_bits_triple, :185); then the state updates LL, ML, OF (:198-207)
+            br.refill();
+            uint32_t obits = of_code ? br.hi >> (32u - of_code) : 0u;
+            br.skip(of_code);
+            br.refill();
+            uint32_t ml_add = ml_bits ? br.hi >> (32u - ml_bits) : 0u; br.skip(ml_bits);
+            uint32_t ll_add = ll_bits ? br.hi >> (32u - ll_bits) : 0u; br.skip(ll_bits);
+            const uint32_t offset = obits + (1u << of_code);
+            const uint32_t ll = s_ll_base[ll_code] + ll_add, ml = s_ml_base[ml_code] + ml_add;
             out[3 * i] = ll; out[3 * i + 1] = ml; out[3 * i + 2] = offset;
             sum_ll += ll; sum_ml += ml;
-            if (i + 1 < nseq) {  // state updates in the order LL, ML, OF (:198-207)
+            if (i + 1 < nseq) {
                 br.refill();
-                sl = tl->e[(sl & 0xffffu) + br.get((sl >> 16) & 0xffu)];
-                sm = tm->e[(sm & 0xffffu) + br.get((sm >> 16) & 0xffu)];
-                so = to->e[(so & 0xffffu) + br.get((so >> 16) & 0xffu)];
+                uint32_t aL = nbL ? br.hi >> (32u - nbL) : 0u; br.skip(nbL);
+                uint32_t aM = nbM ? br.hi >> (32u - nbM) : 0u; br.skip(nbM);
+                uint32_t aO = nbO ? br.hi >> (32u - nbO) : 0u; br.skip(nbO);
+                sl.e = TL[baseL + aL]; sm.e = TM[baseM + aM]; so.e = TO[baseO + aO];
             }
             if (br.p < 0) err = B200Z_ERR_SEQ_NOT_ENOUGH_BYTES_FOR_NUM_SEQUENCES;
         }
@@ -289,7 +483,7 @@ __global__ void k_fse(const BlockDesc *__restrict__ descs, BlockAux *__restrict_
     }
     aux[b].pad = st_seq;
     aux[b].sum_ll = (uint32_t)(sum_ll > 0xffffffffull ? 0xffffffffull : sum_ll);
-    uint64_t total = sum_ml + d.regen_size;
+    uint64_t total = sum_ml + d->regen_size;
     aux[b].out_size = (uint32_t)(total > 0xffffffffull ? 0xffffffffull : total);
 }
 
@@ -443,14 +637,29 @@ int launch_predefined(FseSlot *predef, cudaStream_t s) {
     return (int)cudaGetLastError();
 }
 
+constexpr uint32_t kFseSmem = FSE_BLOCKS_PER_CTA * FSE_TAB_U16 * 2 + (36 + 53) * 4 + 96;
+
+int init_kernels() {
+    cudaError_t e = cudaFuncSetAttribute(k_fse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFseSmem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_huf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HUF_BLOCKS_PER_CTA * HUF_SMEM_PER_BLOCK));
+    return (int)e;
+}
+
 const char *const kStageNames[kNumStages] = {"k_setup", "k_huf", "k_fse", "k_exec"};
 
 // one stage of the pipeline; a stage with nothing to do launches nothing and returns 0
 int launch_stage(const PipelineArgs &a, int stage, cudaStream_t s) {
     switch (stage) {
-        case 0: if (a.nblocks) k_setup<<<cdiv(a.nblocks, 64), 64, 0, s>>>(a.descs, a.aux, a.input, a.nblocks); break;
-        case 1: if (a.nblocks) k_huf<<<cdiv(a.nblocks * 4, 128), 128, 0, s>>>(a.descs, a.aux, a.input, a.lit_scratch, a.nblocks); break;
-        case 2: if (a.nblocks) k_fse<<<cdiv(a.nblocks, 32), 32, 0, s>>>(a.descs, a.aux, a.input, a.seq_scratch, a.nblocks); break;
+        case 0: if (a.nblocks) k_setup<<<cdiv(a.nblocks, SETUP_WARPS), SETUP_WARPS * 32, 0, s>>>(a.descs, a.aux, a.input, a.nblocks); break;
+        case 1:
+            if (a.nblocks)
+                k_huf<<<cdiv(a.nblocks, HUF_BLOCKS_PER_CTA), 32, HUF_BLOCKS_PER_CTA * HUF_SMEM_PER_BLOCK, s>>>(a.descs, a.aux, a.input, a.lit_scratch, a.nblocks);
+            break;
+        case 2:
+            if (a.nblocks)
+                k_fse<<<cdiv(a.nblocks, FSE_BLOCKS_PER_CTA), 32, kFseSmem, s>>>(a.descs, a.aux, a.input, a.seq_scratch, a.nblocks);
+            break;
         case 3:
             if (a.nframes)
                 k_exec<<<cdiv(a.nframes * 32, 128), 128, 0, s>>>(a.descs, a.aux, a.frames, a.states, a.input, a.lit_scratch, a.seq_scratch,

@@ -21,6 +21,7 @@ struct PipelineArgs {
     uint32_t nframes;
 };
 
+int init_kernels();  // per-device function attributes (dynamic shared memory); call once per context
 int launch_predefined(FseSlot *predef, cudaStream_t s);
 constexpr int kNumStages = 4;
 extern const char *const kStageNames[kNumStages];

@@ -160,15 +160,22 @@ B200Z_HDN inline int fse_build_table(const int16_t *probs, uint32_t nprobs, uint
     return 0;
 }
 
+// {base_line | num_bits << 16 | symbol << 24} -> the 16-bit resident form (b200z_types.h)
+B200Z_HDN inline void fse_compact(const uint32_t *wide, uint32_t log, FseTab *tab) {
+    for (uint32_t i = 0; i < (1u << log); i++) tab->e[i] = fse_pack16(log, wide[i] & 0xffffu, (wide[i] >> 16) & 0xffu, wide[i] >> 24);
+    tab->log = log; tab->valid = 1; tab->is_rle = 0;
+}
+
 // FSETable::build_decoder (fse_decoder.rs:116-123) into an FseTab
 B200Z_HDN inline int fse_build_decoder(const uint8_t *src, uint32_t len, uint32_t max_log, uint32_t max_symbol, FseTab *tab, uint32_t &bytes_read) {
     int16_t probs[256];
     uint32_t nprobs, acc_log;
     int e = fse_read_probabilities(src, len, max_log, max_symbol, probs, nprobs, acc_log, bytes_read);
     if (e) return e;
-    e = fse_build_table(probs, nprobs, acc_log, max_symbol, tab->e);
+    uint32_t wide[FSE_MAX_ENTRIES];
+    e = fse_build_table(probs, nprobs, acc_log, max_symbol, wide);
     if (e) return e;
-    tab->log = acc_log; tab->valid = 1; tab->is_rle = 0;
+    fse_compact(wide, acc_log, tab);
     return 0;
 }
 
@@ -182,9 +189,10 @@ B200Z_HDN inline int fse_build_predefined(uint32_t kind /*0 ll,1 of,2 ml*/, FseT
     if (kind == 0) { n = 36; log = 6; maxsym = 35; for (uint32_t i = 0; i < n; i++) probs[i] = LL[i]; }
     else if (kind == 1) { n = 29; log = 5; maxsym = 31; for (uint32_t i = 0; i < n; i++) probs[i] = OF[i]; }
     else { n = 53; log = 6; maxsym = 52; for (uint32_t i = 0; i < n; i++) probs[i] = ML[i]; }
-    int e = fse_build_table(probs, n, log, maxsym, tab->e);
+    uint32_t wide[64];
+    int e = fse_build_table(probs, n, log, maxsym, wide);
     if (e) return e;
-    tab->log = log; tab->valid = 1; tab->is_rle = 0;
+    fse_compact(wide, log, tab);
     return 0;
 }
 
@@ -240,8 +248,8 @@ B200Z_HDN inline int huf_read_weights(const uint8_t *src, uint32_t len, uint8_t 
     return 0;
 }
 
-// build_table_from_weights into packed u16 entries (symbol | num_bits << 8); `entries` may be global memory.
-B200Z_HDN inline int huf_build_table(const uint8_t *weights, uint32_t nweights, uint16_t *entries, uint32_t &max_bits_out) {
+// build_table_from_weights into a HufSlot (serial form: dictionaries on the host; the per-block GPU form is in setup.cuh)
+B200Z_HDN inline int huf_build_table(const uint8_t *weights, uint32_t nweights, HufSlot *slot, uint32_t &max_bits_out) {
     uint32_t weight_sum = 0;
     for (uint32_t i = 0; i < nweights; i++) {
         uint32_t w = weights[i];
@@ -269,8 +277,7 @@ B200Z_HDN inline int huf_build_table(const uint8_t *weights, uint32_t nweights, 
         if (w == 0) continue;
         uint32_t b = max_bits + 1 - w, n = 1u << (max_bits - b), base = rank_idx[b];
         rank_idx[b] += n;
-        uint16_t ent = (uint16_t)((s & 0xffu) | (b << 8));
-        for (uint32_t i = 0; i < n; i++) entries[base + i] = ent;
+        for (uint32_t i = 0; i < n; i++) huf_set(slot, base + i, s & 0xffu, b);
     }
     max_bits_out = max_bits;
     return 0;
@@ -283,7 +290,7 @@ B200Z_HDN inline int huf_build_decoder(const uint8_t *src, uint32_t len, HufSlot
     int e = huf_read_weights(src, len, weights, nweights, bytes_read);
     if (e) return e;
     uint32_t mb;
-    e = huf_build_table(weights, nweights, slot->e, mb);
+    e = huf_build_table(weights, nweights, slot, mb);
     if (e) return e;
     slot->max_bits = mb;
     return 0;
