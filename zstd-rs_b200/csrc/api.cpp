@@ -372,6 +372,7 @@ static int plan_batch(b200z_batch *b, const uint8_t *in, size_t in_len, const b2
         st.hist[0] = dict ? dict->hist[0] : 1; st.hist[1] = dict ? dict->hist[1] : 4; st.hist[2] = dict ? dict->hist[2] : 8;
         TableCursor cur;
         if (dict_idx >= 0) cursor_from_carry(cur, s.carries[dict_idx], (uint32_t)dict_idx);
+        cur.hist_known = true; cur.hist[0] = st.hist[0]; cur.hist[1] = st.hist[1]; cur.hist[2] = st.hist[2];
         fi.first_block_end = b->block_end_bytes.size();
 
         uint64_t pos = consumed, bytes_read = consumed;
@@ -887,6 +888,7 @@ static int fd_decode_blocks_impl(b200z_frame_decoder *d, b200z_read_fn rd, void 
         d->staging.clear();
         TableCursor cur;
         cursor_from_carry(cur, d->carry, 0);
+        cur.hist_known = true; cur.hist[0] = d->state.hist[0]; cur.hist[1] = d->state.hist[1]; cur.hist[2] = d->state.hist[2];
         std::vector<uint64_t> bytes_after;  // bytes_read_counter after each gathered block
         int pending_err = 0, pending_stage = 0;
         bool saw_last = false;

@@ -82,7 +82,10 @@ struct alignas(16) BlockDesc {
     uint32_t host_status;    // error the planner found for this block (stage in bits 16..23), 0 = none
     uint32_t block_in_frame; // ordinal of the block inside its frame
     uint32_t last;           // last block of the frame
-    uint32_t pad0;
+    uint32_t fse_resolves;   // 1: the repeat-offset history at this block's start is known at plan time (first block with
+                             // sequences of its frame), so k_fse resolves offsets itself (do_offset_history) from init_hist
+    uint32_t init_hist[3];
+    uint32_t pad1;
     const HufSlot *huf;      // table the literals decode with (own slot when lit_type == LT_COMPRESSED)
     HufSlot *huf_build;      // where a new Huffman table is built, or null
     const FseTab *ll, *of, *ml;  // tables the sequences decode with (null = uninitialised)
@@ -95,9 +98,10 @@ struct alignas(16) BlockAux {
     uint32_t out_size;       // decompressed size of the block (known after sequence decode)
     uint32_t lit_streams_off;// offset inside the block content where the jump table / single stream starts
     uint32_t seq_bits_off;   // offset inside the block content where the sequence bitstream starts
-    uint64_t out_off;        // position of the block inside its frame's output (after the scan)
     uint32_t sum_ll;         // sum of literal lengths over the block's sequences
-    uint32_t pad;
+    uint32_t pad;            // sequence-stage status (code | stage << 16); literals-stage status is `status`
+    uint32_t hist_after[3];  // offset history after the block, when fse_resolves
+    uint32_t pad2[3];
 };
 
 // Per-frame state: carried between submissions for the streaming mirror, fresh for batch frames.

@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(const BlockDesc *__r
     if (lane == 0) {
         BlockAux a;
         a.status = st_lit;   // literals-stage status; the sequence-stage status travels in `pad` until k_exec orders them
-        a.out_size = 0; a.lit_streams_off = lit_streams_off; a.seq_bits_off = seq_bits_off; a.out_off = 0; a.sum_ll = 0; a.pad = st_seq;
+        a.out_size = 0; a.lit_streams_off = lit_streams_off; a.seq_bits_off = seq_bits_off; a.sum_ll = 0; a.pad = st_seq;
+        a.hist_after[0] = a.hist_after[1] = a.hist_after[2] = 0; a.pad2[0] = a.pad2[1] = a.pad2[2] = 0;
         aux[b] = a;
     }
 }
@@ -168,17 +169,32 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(const BlockDesc *__r
 constexpr uint32_t HUF_BLOCKS_PER_CTA = 8;
 constexpr uint32_t HUF_SMEM_PER_BLOCK = HUF_TABLE_ENTRIES + HUF_TABLE_ENTRIES / 2;  // 3072
 
+// Reversed bit reader for the decode kernels: 64-bit window hi:lo (left aligned) fed by ALIGNED 128-bit loads,
+// double buffered (`nxt` is requested a whole 16-byte group before it is needed, so L2/HBM latency overlaps
+// ~25-50 symbols of decoding).  Same observable behaviour as BitReaderReversed (bit_reader_reverse.rs:6-162):
+// bits below the stream start read as zero and `p` = bits_remaining() goes negative.
 struct HufBits {
-    const uint32_t *base;
-    uint32_t hi, lo;   // unread bits, left aligned in hi:lo
-    int32_t fill;
-    int32_t wi;
-    uint32_t g0;
-    uint32_t nextw;    // word wi-1, already loaded
-    int32_t p;
-    __device__ __forceinline__ uint32_t fetch(int32_t i) const {
+    const uint4 *base;  // 16-byte aligned address at or below the stream start
+    uint4 cur, nxt;     // word groups curg and curg - 1
+    uint32_t hi, lo;    // unread bits, left aligned in hi:lo
+    int32_t fill;       // bits in hi:lo (virtual zeros below the stream start count)
+    int32_t wi;         // 32-bit words [0, wi) not consumed yet
+    int32_t curg;
+    int32_t sw;         // index of the word holding the stream's first byte
+    uint32_t smask;     // mask of the bits of word `sw` that belong to the stream
+    int32_t p;          // bits_remaining()
+    __device__ __forceinline__ uint4 group(int32_t g) const { return g >= 0 ? __ldg(base + g) : make_uint4(0, 0, 0, 0); }
+    __device__ __forceinline__ uint32_t next_word() {
+        int32_t i = wi - 1;
         uint32_t w = 0;
-        if (i >= 0) { w = __ldg(base + i); if (i == 0) w &= ~((1u << g0) - 1u); }
+        if (i >= 0) {
+            int32_t g = i >> 2;
+            if (g != curg) { cur = nxt; curg = g; nxt = group(g - 1); }
+            uint32_t k = (uint32_t)i & 3u;
+            w = k == 0 ? cur.x : (k == 1 ? cur.y : (k == 2 ? cur.z : cur.w));
+            if (i < sw) w = 0; else if (i == sw) w &= smask;
+            wi = i;
+        }
         return w;
     }
     __device__ __forceinline__ bool init(const uint8_t *src, uint32_t len) {
@@ -186,28 +202,29 @@ struct HufBits {
         uint32_t last = src[len - 1];
         if (last == 0) return false;
         uintptr_t a = (uintptr_t)src;
-        base = (const uint32_t *)(a & ~(uintptr_t)3);
-        g0 = (uint32_t)(a & 3) * 8u;
+        base = (const uint4 *)(a & ~(uintptr_t)15);
+        uint32_t g0 = (uint32_t)(a & 15) * 8u;
+        sw = (int32_t)(g0 >> 5);
+        smask = ~((1u << (g0 & 31u)) - 1u);
         p = (int32_t)((len - 1) * 8u + (31u - (uint32_t)__clz((int)last)));
-        hi = lo = 0; fill = 0; wi = 0;
+        hi = lo = 0; fill = 0; wi = 0; curg = -1;
+        cur = nxt = make_uint4(0, 0, 0, 0);
         if (p > 0) {
             uint32_t gtop = g0 + (uint32_t)p - 1u;
-            wi = (int32_t)(gtop >> 5);
-            uint32_t w = fetch(wi);
+            wi = (int32_t)(gtop >> 5) + 1;
+            curg = (wi - 1) >> 2;
+            cur = group(curg); nxt = group(curg - 1);
+            uint32_t w = next_word();
             uint32_t used = (gtop & 31u) + 1u;
             hi = w << (32u - used);
             fill = (int32_t)used;
         }
-        nextw = fetch(wi - 1);
         return true;
     }
     // afterwards fill > 32: at least 32 real-or-virtual bits ready
     __device__ __forceinline__ void refill() {
         if (fill <= 32) {
-            uint32_t w = nextw;
-            --wi;
-            nextw = fetch(wi - 1);
-            // append w below the `fill` valid bits of hi:lo
+            uint32_t w = next_word();
             if (fill == 32) lo = w;
             else if (fill == 0) hi = w;
             else { hi |= w >> fill; lo = w << (32 - fill); }   // fill in [1, 31]
@@ -376,6 +393,23 @@ __constant__ uint8_t c_ll_bits[36] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,
 __constant__ uint32_t c_ml_base[53] = {3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,30,31,32,33,34,35,37,39,41,43,47,51,59,67,83,99,131,259,515,1027,2051,4099,8195,16387,32771,65539};
 __constant__ uint8_t c_ml_bits[53] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,4,5,7,8,9,10,11,12,13,14,15,16};
 
+// do_offset_history (sequence_execution.rs:59-118): offset_value + literal length -> actual offset, history updated
+__device__ __forceinline__ uint32_t offset_history_step(uint32_t of, uint32_t ll, uint32_t &h0, uint32_t &h1, uint32_t &h2) {
+    uint32_t actual;
+    if (ll > 0) {
+        if (of == 1) actual = h0;
+        else if (of == 2) { actual = h1; h1 = h0; h0 = actual; }
+        else if (of == 3) { actual = h2; h2 = h1; h1 = h0; h0 = actual; }
+        else { actual = of - 3; h2 = h1; h1 = h0; h0 = actual; }
+    } else {
+        if (of == 1) { actual = h1; h1 = h0; h0 = actual; }
+        else if (of == 2) { actual = h2; h2 = h1; h1 = h0; h0 = actual; }
+        else if (of == 3) { actual = h0 ? h0 - 1 : 0; h2 = h1; h1 = h0; h0 = actual; }   // saturating_sub, :74
+        else { actual = of - 3; h2 = h1; h1 = h0; h0 = actual; }
+    }
+    return actual;
+}
+
 struct FseState {
     uint32_t e;   // current 16-bit entry
     __device__ __forceinline__ uint32_t sym() const { return e >> 10; }
@@ -437,6 +471,7 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
 
     uint32_t err = 0;
     uint64_t sum_ml = 0, sum_ll = 0;
+    uint32_t h0r = 0, h1r = 0, h2r = 0;
     {
         const uint8_t *src = input + d->src_off + aux[b].seq_bits_off;
         uint32_t len = d->src_size - aux[b].seq_bits_off;
@@ -449,12 +484,16 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
         if (!err) { if (!tl || !tl->valid) err = B200Z_ERR_FSE_TABLE_IS_UNINITIALIZED; else { logL = tl->log; br.refill(); uint32_t i = logL ? br.hi >> (32u - logL) : 0u; br.skip(logL); sl.e = TL[i]; } }
         if (!err) { if (!to || !to->valid) err = B200Z_ERR_FSE_TABLE_IS_UNINITIALIZED; else { logO = to->log; br.refill(); uint32_t i = logO ? br.hi >> (32u - logO) : 0u; br.skip(logO); so.e = TO[i]; } }
         if (!err) { if (!tm || !tm->valid) err = B200Z_ERR_FSE_TABLE_IS_UNINITIALIZED; else { logM = tm->log; br.refill(); uint32_t i = logM ? br.hi >> (32u - logM) : 0u; br.skip(logM); sm.e = TM[i]; } }
-        uint32_t *out = seq_scratch + d->seq_buf_off * 3;
+        uint32_t *out = seq_scratch + d->seq_buf_off * 3;   // 16-byte aligned: the planner rounds seq_buf_off to 4 sequences
         const uint32_t nseq = d->nseq;
-        for (uint32_t i = 0; i < nseq && !err; i++) {
+        uint32_t stage[12];
+        const bool resolve = d->fse_resolves != 0;
+        uint32_t h0 = d->init_hist[0], h1 = d->init_hist[1], h2 = d->init_hist[2];
+        // one sequence; `last` suppresses the state update exactly like `target.len() < num_sequences` (:198)
+        auto one = [&](uint32_t &ll, uint32_t &ml, uint32_t &offset, bool last) {
             const uint32_t ll_code = sl.sym(), ml_code = sm.sym(), of_code = so.sym();
-            if (ll_code > 35 || ml_code > 52) { err = B200Z_ERR_REFERENCE_WOULD_PANIC; break; }  // unreachable!: tables cap the symbols
-            if (of_code > 31) { err = B200Z_ERR_SEQ_UNSUPPORTED_OFFSET; break; }
+            if (ll_code > 35 || ml_code > 52) { err = B200Z_ERR_REFERENCE_WOULD_PANIC; return; }  // unreachable!: tables cap the symbols
+            if (of_code > 31) { err = B200Z_ERR_SEQ_UNSUPPORTED_OFFSET; return; }
             const uint32_t ll_bits = s_ll_bits[ll_code], ml_bits = s_ml_bits[ml_code];
             uint32_t nbL, nbM, nbO, baseL, baseM, baseO;
             sl.decode(logL, nbL, baseL); sm.decode(logM, nbM, baseM); so.decode(logO, nbO, baseO);
@@ -465,11 +504,11 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
             br.refill();
             uint32_t ml_add = ml_bits ? br.hi >> (32u - ml_bits) : 0u; br.skip(ml_bits);
             uint32_t ll_add = ll_bits ? br.hi >> (32u - ll_bits) : 0u; br.skip(ll_bits);
-            const uint32_t offset = obits + (1u << of_code);
-            const uint32_t ll = s_ll_base[ll_code] + ll_add, ml = s_ml_base[ml_code] + ml_add;
-            out[3 * i] = ll; out[3 * i + 1] = ml; out[3 * i + 2] = offset;
+            offset = obits + (1u << of_code);
+            ll = s_ll_base[ll_code] + ll_add; ml = s_ml_base[ml_code] + ml_add;
             sum_ll += ll; sum_ml += ml;
-            if (i + 1 < nseq) {
+            if (resolve) offset = offset_history_step(offset, ll, h0, h1, h2);   // `of` becomes the actual offset
+            if (!last) {
                 br.refill();
                 uint32_t aL = nbL ? br.hi >> (32u - nbL) : 0u; br.skip(nbL);
                 uint32_t aM = nbM ? br.hi >> (32u - nbM) : 0u; br.skip(nbM);
@@ -477,18 +516,46 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
                 sl.e = TL[baseL + aL]; sm.e = TM[baseM + aM]; so.e = TO[baseO + aO];
             }
             if (br.p < 0) err = B200Z_ERR_SEQ_NOT_ENOUGH_BYTES_FOR_NUM_SEQUENCES;
+        };
+        uint32_t i = 0;
+        for (; i + 4 < nseq && !err; i += 4) {   // groups of four, none of them the last sequence
+#pragma unroll
+            for (int q = 0; q < 4; q++) { if (!err) one(stage[3 * q], stage[3 * q + 1], stage[3 * q + 2], false); }
+            if (!err) {
+                uint4 *o4 = reinterpret_cast<uint4 *>(out + 3 * i);
+                o4[0] = make_uint4(stage[0], stage[1], stage[2], stage[3]);
+                o4[1] = make_uint4(stage[4], stage[5], stage[6], stage[7]);
+                o4[2] = make_uint4(stage[8], stage[9], stage[10], stage[11]);
+            }
+        }
+        for (; i < nseq && !err; i++) {
+            uint32_t ll = 0, ml = 0, of = 0;
+            one(ll, ml, of, i + 1 == nseq);
+            if (!err || err == B200Z_ERR_SEQ_NOT_ENOUGH_BYTES_FOR_NUM_SEQUENCES) { out[3 * i] = ll; out[3 * i + 1] = ml; out[3 * i + 2] = of; }
         }
         if (!err && br.p > 0) err = B200Z_ERR_SEQ_EXTRA_BITS;
         if (err) st_seq = mk_status(err, B200Z_STAGE_SEQUENCES);
+        h0r = h0; h1r = h1; h2r = h2;
     }
     aux[b].pad = st_seq;
+    if (d->fse_resolves) { aux[b].hist_after[0] = h0r; aux[b].hist_after[1] = h1r; aux[b].hist_after[2] = h2r; }
     aux[b].sum_ll = (uint32_t)(sum_ll > 0xffffffffull ? 0xffffffffull : sum_ll);
     uint64_t total = sum_ml + d->regen_size;
     aux[b].out_size = (uint32_t)(total > 0xffffffffull ? 0xffffffffull : total);
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_exec: one warp per frame; blocks in order.
+// k_exec: LZ77 execution.  One warp per frame, blocks in order, 32 sequences per step.
+//
+// Fast path (per batch of 32 sequences, lane j = sequence j): warp scans give every sequence its literal and
+// match positions; a bitmask of match starts in shared memory lets each OUTPUT byte find its owner with one
+// popc; the batch's bytes are then produced row by row (32 consecutive bytes = one coalesced store): literal
+// bytes first, then match bytes whose source byte is final, looping inside the row until it is complete
+// (sources always precede destinations, so the lowest pending byte is always ready).  Overlapping matches use
+// source = start + (k mod offset), the byte-order-preserving form of repeat_in_chunks (decode_buffer.rs:113-141).
+// Anything unusual in a batch (dictionary reach, long runs, zero offsets, literal under-run, capacity) sends
+// that batch to the exact sequential path below, which is execute_sequences / DecodeBuffer::repeat statement by
+// statement.
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint32_t n, uint32_t lane) {
     for (uint32_t k = lane; k < n; k += 32) dst[k] = src[k];
@@ -496,28 +563,87 @@ __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint
 __device__ __forceinline__ void warp_fill(uint8_t *dst, uint8_t v, uint32_t n, uint32_t lane) {
     for (uint32_t k = lane; k < n; k += 32) dst[k] = v;
 }
-// LZ77 match copy with byte-order-preserving overlap: byte k comes from src[k mod off] (repeat_in_chunks,
-// decode_buffer.rs:113-141: chunks of `offset` bytes re-read what the previous chunk wrote)
 __device__ __forceinline__ void warp_match(uint8_t *dst, const uint8_t *src, uint32_t n, uint32_t off, uint32_t lane) {
     if (off >= n) { for (uint32_t k = lane; k < n; k += 32) dst[k] = src[k]; }
     else { for (uint32_t k = lane; k < n; k += 32) dst[k] = src[k % off]; }
 }
 
-__global__ void k_exec(const BlockDesc *__restrict__ descs, const BlockAux *__restrict__ aux, const FrameDesc *__restrict__ frames,
-                       FrameState *__restrict__ states, const uint8_t *__restrict__ input, const uint8_t *__restrict__ lit_scratch,
-                       const uint32_t *__restrict__ seq_scratch, uint8_t *__restrict__ output, uint64_t output_cap, uint32_t nframes) {
-    uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t lane = threadIdx.x & 31;
+struct ExecState {
+    uint32_t h0, h1, h2;
+    uint64_t produced, counter, drained, cap;
+    uint32_t litpos;
+};
+struct LitSrc { const uint8_t *p; uint32_t rle; uint8_t byte; uint32_t regen; };
+
+// exact sequential execution of up to 32 sequences held one per lane (my_ll/my_ml/my_of); `resolved` = offsets
+// already went through do_offset_history.  Returns 0 or an error code.
+__device__ uint32_t exec_batch_exact(ExecState &st, const LitSrc &lit, const FrameDesc &fd, uint8_t *out, uint32_t nb, uint32_t my_ll, uint32_t my_ml,
+                                     uint32_t my_of, bool resolved, uint32_t lane) {
+    for (uint32_t j = 0; j < nb; j++) {
+        uint32_t ll = __shfl_sync(0xffffffffu, my_ll, j), ml = __shfl_sync(0xffffffffu, my_ml, j), of = __shfl_sync(0xffffffffu, my_of, j);
+        if (ll > 0) {
+            if ((uint64_t)st.litpos + ll > lit.regen) return B200Z_ERR_EXEC_NOT_ENOUGH_BYTES_FOR_SEQUENCE;
+            if (st.produced + ll > st.cap) return B200Z_ERR_TARGET_TOO_SMALL;
+            if (lit.rle) warp_fill(out + st.produced, lit.byte, ll, lane); else warp_copy(out + st.produced, lit.p + st.litpos, ll, lane);
+            st.litpos += ll; st.produced += ll; st.counter += ll;
+        }
+        uint32_t actual = resolved ? of : offset_history_step(of, ll, st.h0, st.h1, st.h2);
+        if (actual == 0) return B200Z_ERR_EXEC_ZERO_OFFSET;
+        if (ml > 0) {
+            if (st.produced + ml > st.cap) return B200Z_ERR_TARGET_TOO_SMALL;
+            __syncwarp();
+            uint64_t buf_len = st.produced - st.drained;
+            if ((uint64_t)actual > buf_len) {
+                // repeat_from_dict (decode_buffer.rs:143-179)
+                if (st.counter <= fd.window_size) {
+                    uint64_t from_dict = (uint64_t)actual - buf_len;
+                    if (from_dict > fd.dict_len) return B200Z_ERR_EXEC_NOT_ENOUGH_BYTES_IN_DICTIONARY;
+                    if (from_dict < ml) {
+                        warp_copy(out + st.produced, fd.dict + fd.dict_len - from_dict, (uint32_t)from_dict, lane);
+                        st.produced += from_dict; st.counter += from_dict;
+                        __syncwarp();
+                        uint32_t rest = ml - (uint32_t)from_dict;
+                        uint64_t bl2 = st.produced - st.drained;  // repeat(self.buffer.len(), rest): from the buffer start
+                        warp_match(out + st.produced, out + st.drained, rest, bl2 > 0xffffffffull ? 0xffffffffu : (uint32_t)bl2, lane);
+                        st.produced += rest; st.counter += rest;
+                    } else {
+                        warp_copy(out + st.produced, fd.dict + fd.dict_len - from_dict, ml, lane);
+                        st.produced += ml;  // sic: total_output_counter not advanced on this branch (:166-171)
+                    }
+                } else return B200Z_ERR_EXEC_OFFSET_TOO_BIG;
+            } else {
+                warp_match(out + st.produced, out + st.produced - actual, ml, actual, lane);
+                st.produced += ml; st.counter += ml;
+            }
+            __syncwarp();
+        }
+    }
+    return 0;
+}
+
+constexpr uint32_t EXEC_WARPS = 4;
+constexpr uint32_t EXEC_MAX_RUN = 127;                      // longest literal run / match the fast path takes
+constexpr uint32_t EXEC_MASK_WORDS = (32 * 2 * EXEC_MAX_RUN + 31) / 32 + 1;
+
+__global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const BlockDesc *__restrict__ descs, const BlockAux *__restrict__ aux,
+                                                        const FrameDesc *__restrict__ frames, FrameState *__restrict__ states,
+                                                        const uint8_t *__restrict__ input, const uint8_t *__restrict__ lit_scratch,
+                                                        const uint32_t *__restrict__ seq_scratch, uint8_t *__restrict__ output, uint64_t output_cap,
+                                                        uint32_t nframes) {
+    __shared__ uint32_t s_mask[EXEC_WARPS][EXEC_MASK_WORDS];
+    const uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31, lt = lanemask_lt(), le = lt | (1u << lane);
     if (f >= nframes) return;
+    uint32_t *mask = s_mask[threadIdx.x >> 5];
     const FrameDesc &fd = frames[f];
-    FrameState st = states[f];
-    uint32_t h0 = st.hist[0], h1 = st.hist[1], h2 = st.hist[2];
-    uint64_t produced = st.produced, counter = st.counter;
-    const uint64_t drained = st.drained;
-    uint64_t cap = fd.out_cap;
-    if (fd.out_off > output_cap) cap = 0; else if (cap > output_cap - fd.out_off) cap = output_cap - fd.out_off;
+    FrameState fs = states[f];
+    ExecState st;
+    st.h0 = fs.hist[0]; st.h1 = fs.hist[1]; st.h2 = fs.hist[2];
+    st.produced = fs.produced; st.counter = fs.counter; st.drained = fs.drained;
+    st.cap = fd.out_cap;
+    if (fd.out_off > output_cap) st.cap = 0; else if (st.cap > output_cap - fd.out_off) st.cap = output_cap - fd.out_off;
     uint8_t *out = output + fd.out_off;
-    uint32_t status = st.status, err_block = st.error_block, blocks_done = st.blocks_done;
+    uint32_t status = fs.status, err_block = fs.error_block, blocks_done = fs.blocks_done;
 
     for (uint32_t bi = 0; bi < fd.nblocks && !status; bi++) {
         const uint32_t b = fd.first_block + bi;
@@ -534,87 +660,120 @@ __global__ void k_exec(const BlockDesc *__restrict__ descs, const BlockAux *__re
         if (bs) { status = bs; err_block = d.block_in_frame; break; }
 
         if (d.btype == BT_RAW) {
-            if (produced + d.raw_size > cap) { status = mk_status(B200Z_ERR_TARGET_TOO_SMALL, B200Z_STAGE_DRAIN); err_block = d.block_in_frame; break; }
-            warp_copy(out + produced, input + d.src_off, d.raw_size, lane);
-            produced += d.raw_size;   // extend_from_reader: total_output_counter untouched (decode_buffer.rs:66-72)
+            if (st.produced + d.raw_size > st.cap) { status = mk_status(B200Z_ERR_TARGET_TOO_SMALL, B200Z_STAGE_DRAIN); err_block = d.block_in_frame; break; }
+            warp_copy(out + st.produced, input + d.src_off, d.raw_size, lane);
+            st.produced += d.raw_size;   // extend_from_reader: total_output_counter untouched (decode_buffer.rs:66-72)
         } else if (d.btype == BT_RLE) {
-            if (produced + d.raw_size > cap) { status = mk_status(B200Z_ERR_TARGET_TOO_SMALL, B200Z_STAGE_DRAIN); err_block = d.block_in_frame; break; }
-            warp_fill(out + produced, input[d.src_off], d.raw_size, lane);
-            produced += d.raw_size;
+            if (st.produced + d.raw_size > st.cap) { status = mk_status(B200Z_ERR_TARGET_TOO_SMALL, B200Z_STAGE_DRAIN); err_block = d.block_in_frame; break; }
+            warp_fill(out + st.produced, input[d.src_off], d.raw_size, lane);
+            st.produced += d.raw_size;
         } else {
-            const uint8_t *lit;
-            uint32_t lit_rle = 0; uint8_t rle_byte = 0;
-            if (d.lit_type == LT_RAW) lit = input + d.src_off + d.lit_off;
-            else if (d.lit_type == LT_RLE) { lit = nullptr; lit_rle = 1; rle_byte = input[d.src_off + d.lit_off]; }
-            else lit = lit_scratch + d.lit_buf_off;
-            const uint32_t regen = d.regen_size;
-            uint32_t litpos = 0, e = 0;
+            LitSrc lit;
+            lit.rle = 0; lit.byte = 0; lit.regen = d.regen_size;
+            if (d.lit_type == LT_RAW) lit.p = input + d.src_off + d.lit_off;
+            else if (d.lit_type == LT_RLE) { lit.p = nullptr; lit.rle = 1; lit.byte = input[d.src_off + d.lit_off]; }
+            else lit.p = lit_scratch + d.lit_buf_off;
+            st.litpos = 0;
+            uint32_t e = 0;
+            const bool resolved = d.fse_resolves != 0;
             const uint32_t *seqs = seq_scratch + d.seq_buf_off * 3;
+            __syncwarp();
             for (uint32_t base = 0; base < d.nseq && !e; base += 32) {
-                uint32_t nb = d.nseq - base < 32 ? d.nseq - base : 32;
-                uint32_t my_ll = 0, my_ml = 0, my_of = 0;
+                const uint32_t nb = d.nseq - base < 32 ? d.nseq - base : 32;
+                uint32_t my_ll = 0, my_ml = 0, my_of = 1;
                 if (lane < nb) { const uint32_t *s = seqs + (uint64_t)(base + lane) * 3; my_ll = s[0]; my_ml = s[1]; my_of = s[2]; }
-                for (uint32_t j = 0; j < nb; j++) {
-                    uint32_t ll = __shfl_sync(0xffffffffu, my_ll, j), ml = __shfl_sync(0xffffffffu, my_ml, j), of = __shfl_sync(0xffffffffu, my_of, j);
-                    if (ll > 0) {
-                        if ((uint64_t)litpos + ll > regen) { e = B200Z_ERR_EXEC_NOT_ENOUGH_BYTES_FOR_SEQUENCE; break; }
-                        if (produced + ll > cap) { e = B200Z_ERR_TARGET_TOO_SMALL; break; }
-                        if (lit_rle) warp_fill(out + produced, rle_byte, ll, lane); else warp_copy(out + produced, lit + litpos, ll, lane);
-                        litpos += ll; produced += ll; counter += ll;
+                // inclusive scans of ll and ll + ml
+                uint32_t lit_end = my_ll, out_end = my_ll + my_ml;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    uint32_t a = __shfl_up_sync(0xffffffffu, lit_end, dd), c = __shfl_up_sync(0xffffffffu, out_end, dd);
+                    if ((int)lane >= dd) { lit_end += a; out_end += c; }
+                }
+                const uint32_t T = __shfl_sync(0xffffffffu, out_end, 31), L = __shfl_sync(0xffffffffu, lit_end, 31);
+                // offsets for the fast path must be resolved: blocks whose history is not a plan-time constant resolve here
+                uint32_t my_off = my_of;
+                bool fast = true;
+                if (!resolved) {
+                    // 32 cheap scalar steps (sequence_execution.rs:59-118); keeps st.h* exact for the next batch
+                    uint32_t h0 = st.h0, h1 = st.h1, h2 = st.h2;
+                    for (uint32_t j = 0; j < nb; j++) {
+                        uint32_t ll = __shfl_sync(0xffffffffu, my_ll, j), of = __shfl_sync(0xffffffffu, my_of, j);
+                        uint32_t actual = offset_history_step(of, ll, h0, h1, h2);
+                        if (lane == j) my_off = actual;
                     }
-                    // do_offset_history (sequence_execution.rs:59-118)
-                    uint32_t actual;
-                    if (ll > 0) {
-                        if (of == 1) actual = h0;
-                        else if (of == 2) { actual = h1; h1 = h0; h0 = actual; }
-                        else if (of == 3) { actual = h2; h2 = h1; h1 = h0; h0 = actual; }
-                        else { actual = of - 3; h2 = h1; h1 = h0; h0 = actual; }
-                    } else {
-                        if (of == 1) { actual = h1; h1 = h0; h0 = actual; }
-                        else if (of == 2) { actual = h2; h2 = h1; h1 = h0; h0 = actual; }
-                        else if (of == 3) { actual = h0 ? h0 - 1 : 0; h2 = h1; h1 = h0; h0 = actual; }
-                        else { actual = of - 3; h2 = h1; h1 = h0; h0 = actual; }
+                    // committed only if the fast path is taken (the exact path redoes the steps itself)
+                    uint32_t m_start = out_end - my_ml;
+                    bool ok = lane >= nb || (my_ll <= EXEC_MAX_RUN && my_ml <= EXEC_MAX_RUN && my_off != 0 &&
+                                             (uint64_t)my_off <= st.produced - st.drained + m_start);
+                    fast = __all_sync(0xffffffffu, ok) && (uint64_t)st.litpos + L <= lit.regen && st.produced + T <= st.cap;
+                    if (fast) { st.h0 = h0; st.h1 = h1; st.h2 = h2; }
+                } else {
+                    uint32_t m_start = out_end - my_ml;
+                    bool ok = lane >= nb || (my_ll <= EXEC_MAX_RUN && my_ml <= EXEC_MAX_RUN && my_off != 0 &&
+                                             (uint64_t)my_off <= st.produced - st.drained + m_start);
+                    fast = __all_sync(0xffffffffu, ok) && (uint64_t)st.litpos + L <= lit.regen && st.produced + T <= st.cap;
+                }
+                if (!fast) {
+                    e = exec_batch_exact(st, lit, fd, out, nb, my_ll, my_ml, my_of, resolved, lane);
+                    continue;
+                }
+                // ---------------- fast path
+                const uint32_t m_start = out_end - my_ml;            // batch-relative start of my match
+                const uint32_t pack = m_start | (out_end << 16);       // T <= 8128 < 2^16
+                const uint32_t l_start = st.litpos + lit_end - my_ll;  // literal index of my literal run
+                const uint32_t nrows = (T + 31) >> 5;
+                for (uint32_t w = lane; w < nrows; w += 32) mask[w] = 0;
+                __syncwarp();
+                if (lane < nb) atomicOr(&mask[m_start >> 5], 1u << (m_start & 31u));
+                __syncwarp();
+                uint8_t *bout = out + st.produced;
+                uint32_t before = 0;   // match starts in earlier rows
+                for (uint32_t r = 0; r < nrows; r++) {
+                    const uint32_t q = (r << 5) + lane;
+                    const uint32_t word = mask[r];
+                    const uint32_t jm = before + __popc(word & le);   // match starts at or before q
+                    before += __popc(word);
+                    const uint32_t c = jm ? jm - 1 : 0;
+                    const uint32_t pk = __shfl_sync(0xffffffffu, pack, c);
+                    const uint32_t off = __shfl_sync(0xffffffffu, my_off, c);
+                    const uint32_t ls = __shfl_sync(0xffffffffu, l_start, jm & 31u);
+                    const bool valid = q < T;
+                    const uint32_t mend = pk >> 16, mst = pk & 0xffffu;
+                    const bool is_match = valid && jm && q < mend;
+                    if (valid && !is_match) {
+                        // literal run of sequence jm starts where match jm-1 ended (or at the batch start)
+                        uint32_t li = ls + (q - (jm ? mend : 0u));
+                        bout[q] = lit.rle ? lit.byte : lit.p[li];
                     }
-                    if (actual == 0) { e = B200Z_ERR_EXEC_ZERO_OFFSET; break; }
-                    if (ml > 0) {
-                        if (produced + ml > cap) { e = B200Z_ERR_TARGET_TOO_SMALL; break; }
-                        __syncwarp();
-                        uint64_t buf_len = produced - drained;
-                        if ((uint64_t)actual > buf_len) {
-                            // repeat_from_dict (decode_buffer.rs:143-179)
-                            if (counter <= fd.window_size) {
-                                uint64_t from_dict = (uint64_t)actual - buf_len;
-                                if (from_dict > fd.dict_len) { e = B200Z_ERR_EXEC_NOT_ENOUGH_BYTES_IN_DICTIONARY; break; }
-                                if (from_dict < ml) {
-                                    warp_copy(out + produced, fd.dict + fd.dict_len - from_dict, (uint32_t)from_dict, lane);
-                                    produced += from_dict; counter += from_dict;
-                                    __syncwarp();
-                                    uint32_t rest = ml - (uint32_t)from_dict;
-                                    uint64_t bl2 = produced - drained;  // repeat(self.buffer.len(), rest): from the buffer start
-                                    warp_match(out + produced, out + drained, rest, bl2 > 0xffffffffull ? 0xffffffffu : (uint32_t)bl2, lane);
-                                    produced += rest; counter += rest;
-                                } else {
-                                    warp_copy(out + produced, fd.dict + fd.dict_len - from_dict, ml, lane);
-                                    produced += ml;  // sic: total_output_counter not advanced on this branch (:166-171)
-                                }
-                            } else { e = B200Z_ERR_EXEC_OFFSET_TOO_BIG; break; }
-                        } else {
-                            warp_match(out + produced, out + produced - actual, ml, actual, lane);
-                            produced += ml; counter += ml;
+                    uint32_t pending = __ballot_sync(0xffffffffu, is_match);
+                    if (pending) {
+                        uint32_t kk = q - mst;
+                        if (is_match && kk >= off) kk %= off;
+                        // source position relative to the batch start (may be negative: earlier output)
+                        const int32_t sp = (int32_t)mst - (int32_t)off + (int32_t)kk;
+                        const int32_t row0 = (int32_t)(r << 5);
+                        bool mine = is_match;
+                        while (pending) {
+                            __syncwarp();
+                            bool ready = mine && (sp < row0 || !((pending >> (sp - row0)) & 1u));
+                            if (ready) { bout[q] = bout[sp]; mine = false; }
+                            pending &= ~__ballot_sync(0xffffffffu, ready);
                         }
-                        __syncwarp();
                     }
                 }
+                __syncwarp();
+                st.produced += T; st.counter += T; st.litpos += L;
             }
-            if (!e && litpos < regen) {
-                uint32_t rest = regen - litpos;
-                if (produced + rest > cap) e = B200Z_ERR_TARGET_TOO_SMALL;
+            if (!e && st.litpos < lit.regen) {
+                uint32_t rest = lit.regen - st.litpos;
+                if (st.produced + rest > st.cap) e = B200Z_ERR_TARGET_TOO_SMALL;
                 else {
-                    if (lit_rle) warp_fill(out + produced, rle_byte, rest, lane); else warp_copy(out + produced, lit + litpos, rest, lane);
-                    produced += rest; counter += rest;
+                    if (lit.rle) warp_fill(out + st.produced, lit.byte, rest, lane); else warp_copy(out + st.produced, lit.p + st.litpos, rest, lane);
+                    st.produced += rest; st.counter += rest;
                 }
             }
             if (e) { status = mk_status(e, e == B200Z_ERR_TARGET_TOO_SMALL ? B200Z_STAGE_DRAIN : B200Z_STAGE_EXECUTE); err_block = d.block_in_frame; break; }
+            if (resolved && d.nseq) { st.h0 = aux[b].hist_after[0]; st.h1 = aux[b].hist_after[1]; st.h2 = aux[b].hist_after[2]; }
         }
         __syncwarp();
         blocks_done++;
@@ -622,8 +781,8 @@ __global__ void k_exec(const BlockDesc *__restrict__ descs, const BlockAux *__re
     if (!status && fd.host_status) { status = fd.host_status & 0x00ffffffu; err_block = blocks_done; }
     if (lane == 0) {
         FrameState &o = states[f];
-        o.hist[0] = h0; o.hist[1] = h1; o.hist[2] = h2;
-        o.status = status; o.produced = produced; o.counter = counter; o.error_block = err_block; o.blocks_done = blocks_done;
+        o.hist[0] = st.h0; o.hist[1] = st.h1; o.hist[2] = st.h2;
+        o.status = status; o.produced = st.produced; o.counter = st.counter; o.error_block = err_block; o.blocks_done = blocks_done;
     }
 }
 
@@ -662,7 +821,7 @@ int launch_stage(const PipelineArgs &a, int stage, cudaStream_t s) {
             break;
         case 3:
             if (a.nframes)
-                k_exec<<<cdiv(a.nframes * 32, 128), 128, 0, s>>>(a.descs, a.aux, a.frames, a.states, a.input, a.lit_scratch, a.seq_scratch,
+                k_exec<<<cdiv(a.nframes, EXEC_WARPS), EXEC_WARPS * 32, 0, s>>>(a.descs, a.aux, a.frames, a.states, a.input, a.lit_scratch, a.seq_scratch,
                                                                 a.output, a.output_cap, a.nframes);
             break;
         default: break;
