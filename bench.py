@@ -230,7 +230,7 @@ def main():
     h_in = torch.from_numpy(fs.comp.copy()).pin_memory()
     h_out = torch.empty(D + 64, dtype=torch.uint8).pin_memory()
     e2e_ms = []
-    for i in range(1 + args.e2e_steps):
+    for i in range((1 + args.e2e_steps) if args.e2e_steps > 0 else 0):
         barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
         r = pkg.decode_frames(ctx, h_in, io, h_out)
@@ -238,8 +238,9 @@ def main():
         assert (r["status"] == 0).all()
         if i > 0:
             e2e_ms.append(dt)
-    assert np.array_equal(h_out[:D].numpy(), fs.plain), "e2e output differs"
-    te = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device="cuda")
+    if e2e_ms:
+        assert np.array_equal(h_out[:D].numpy(), fs.plain), "e2e output differs"
+    te = torch.tensor([float(np.mean(e2e_ms)) if e2e_ms else float("nan")], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = D * world / (float(te.item()) * 1e-3) / GB
