@@ -169,6 +169,97 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(const BlockDesc *__r
 constexpr uint32_t HUF_BLOCKS_PER_CTA = 8;
 constexpr uint32_t HUF_SMEM_PER_BLOCK = HUF_TABLE_ENTRIES + HUF_TABLE_ENTRIES / 2;  // 3072
 
+// ---- PTX helpers with defined behaviour for shift counts >= 32 (shl/shr clamp the count, funnelshift .clamp)
+__device__ __forceinline__ uint32_t shr_c(uint32_t a, uint32_t n) { uint32_t r; asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(n)); return r; }
+__device__ __forceinline__ uint32_t shl_c(uint32_t a, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(n)); return r; }
+__device__ __forceinline__ uint32_t fsl_c(uint32_t lo, uint32_t hi, uint32_t n) { return __funnelshift_lc(lo, hi, n); }
+
+// Reversed bit reader whose words come from a per-lane ring in shared memory (32 words = 8 groups of 16 bytes)
+// that cp.async keeps filled 7 groups ahead of consumption: the refill is two shifts and an LDS, never a global
+// load on the dependency chain.  Branch-free: every operation is predicated, so 32 lanes decoding 32 different
+// blocks stay converged.  Same observable behaviour as BitReaderReversed (bit_reader_reverse.rs:6-162).
+constexpr uint32_t RING_STRIDE = 144;   // bytes per lane: 128 + 16 so that lanes start 4 banks apart
+struct RingBits {
+    const uint4 *base;   // 16-byte aligned address at or below the stream start
+    uint32_t ring;       // shared-memory byte address (cvta) of this lane's ring
+    uint32_t hi, lo;
+    int32_t fill;
+    int32_t wi;          // words [0, wi) not consumed; nextw holds word wi - 1
+    int32_t next_g;      // next group to request (descending); the group being consumed is next_g + 8
+    int32_t sw;
+    uint32_t smask;
+    uint32_t nextw;
+    int32_t p;
+
+    __device__ __forceinline__ void request(int32_t g) {
+        uint32_t dst = ring + (((uint32_t)g & 7u) << 4);
+        const uint4 *src = base + g;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;" ::"r"(dst), "l"(src) : "memory");
+    }
+    __device__ __forceinline__ uint32_t lds(uint32_t addr) const { uint32_t w; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr) : "memory"); return w; }
+    __device__ __forceinline__ void sts(uint32_t addr, uint32_t w) const { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(w) : "memory"); }
+    // group 0 holds the stream's first byte: zero what lies below it, once, after it has landed
+    __device__ __forceinline__ void fixup_group0() {
+        for (int32_t i = 0; i <= sw; i++) { uint32_t a = ring + ((uint32_t)i << 2); sts(a, i < sw ? 0u : (lds(a) & smask)); }
+    }
+    __device__ __forceinline__ uint32_t word(int32_t i) const { uint32_t w = lds(ring + (((uint32_t)i & 31u) << 2)); return i >= 0 ? w : 0u; }
+    __device__ __forceinline__ bool init(const uint8_t *src, uint32_t len, uint32_t ring_addr) {
+        ring = ring_addr;
+        hi = lo = 0; fill = 0; wi = 0; next_g = -9; nextw = 0; p = 0; sw = 0; smask = 0; base = nullptr;
+        if (len == 0) return false;
+        uint32_t last = src[len - 1];
+        if (last == 0) return false;
+        uintptr_t a = (uintptr_t)src;
+        base = (const uint4 *)(a & ~(uintptr_t)15);
+        uint32_t g0 = (uint32_t)(a & 15) * 8u;
+        sw = (int32_t)(g0 >> 5);
+        smask = ~((1u << (g0 & 31u)) - 1u);
+        p = (int32_t)((len - 1) * 8u + (31u - (uint32_t)__clz((int)last)));
+        if (p > 0) {
+            uint32_t gtop = g0 + (uint32_t)p - 1u;
+            wi = (int32_t)(gtop >> 5) + 1;
+            int32_t gt = (wi - 1) >> 2;
+            for (int32_t g = gt; g > gt - 8; g--) if (g >= 0) request(g);
+            next_g = gt - 8;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (gt < 8) fixup_group0();
+            uint32_t w = word(wi - 1);
+            wi -= 1;
+            uint32_t used = (gtop & 31u) + 1u;
+            hi = w << (32u - used);
+            fill = (int32_t)used;
+            nextw = word(wi - 1);
+        }
+        return true;
+    }
+    // afterwards fill > 32.  Predicated, no branch, no global access.
+    __device__ __forceinline__ void refill() {
+        const bool need = fill <= 32;
+        const uint32_t w = need ? nextw : 0u;
+        hi |= shr_c(w, (uint32_t)fill);
+        lo |= shl_c(w, 32u - (uint32_t)fill);
+        fill += need ? 32 : 0;
+        wi -= (need && wi > 0) ? 1 : 0;
+        nextw = need ? word(wi - 1) : nextw;
+    }
+    // keeps the ring 7 groups ahead; call at least once per 4 consumed words (once per sequence / per 4 symbols)
+    __device__ __forceinline__ void service() {
+        const int32_t cur_g = (wi - 1) >> 2;             // group of the preloaded word (arithmetic shift: -1 when done)
+        if (cur_g < next_g + 8) {                        // consumption left group next_g + 8: its slot is free
+            if (next_g >= 0) request(next_g);
+            next_g -= 1;
+            asm volatile("cp.async.wait_group 6;" ::: "memory");
+            if (cur_g == 1) fixup_group0();   // group 0 has landed (groups >= cur_g - 1 are complete) and nothing of it was read yet
+        }
+    }
+    __device__ __forceinline__ void skip(uint32_t n) {  // n <= 32
+        hi = fsl_c(lo, hi, n);
+        lo = shl_c(lo, n);
+        fill -= (int32_t)n;
+        p -= (int32_t)n;
+    }
+};
+
 // Reversed bit reader for the decode kernels: 64-bit window hi:lo (left aligned) fed by ALIGNED 128-bit loads,
 // double buffered (`nxt` is requested a whole 16-byte group before it is needed, so L2/HBM latency overlaps
 // ~25-50 symbols of decoding).  Same observable behaviour as BitReaderReversed (bit_reader_reverse.rs:6-162):
@@ -238,6 +329,44 @@ struct HufBits {
         p -= (int32_t)n;
     }
 };
+
+// Fast huff0 stream: decodes exactly `cap` symbols with a count-based, branch-free loop (no per-symbol position
+// checks); the stream was "regular" iff it is then exhausted exactly (every code consumes >= 1 bit, so ending on
+// bits_remaining == 0 after `cap` symbols is equivalent to the reference's loop stopping there,
+// literals_section_decoder.rs:112-121).  Returns true when regular; otherwise the caller replays with huf_stream2.
+__device__ __forceinline__ bool huf_stream_fast(const uint8_t *__restrict__ tsym, const uint8_t *__restrict__ tnb, uint32_t mb,
+                                                const uint8_t *src, uint32_t len, uint8_t *dst, uint32_t cap, uint32_t ring_addr) {
+    RingBits br;
+    if (!br.init(src, len, ring_addr)) return false;
+    const uint32_t sh = 32u - mb;
+    uint32_t n = 0;
+    auto sym1 = [&]() -> uint32_t {
+        uint32_t idx = br.hi >> sh;
+        uint32_t s = tsym[idx];
+        br.skip((tnb[idx >> 1] >> ((idx & 1u) * 4u)) & 15u);
+        return s;
+    };
+    // scalar head until dst + n is 16-byte aligned
+    uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
+    if (head > cap) head = cap;
+    for (; n < head; n++) { br.refill(); dst[n] = (uint8_t)sym1(); br.service(); }
+    for (; n + 16 <= cap; n += 16) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            br.refill();
+            uint32_t s0 = sym1(), s1 = sym1();
+            br.refill();
+            uint32_t s2 = sym1(), s3 = sym1();
+            br.service();
+            w[q] = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+        }
+        *reinterpret_cast<uint4 *>(dst + n) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    for (; n < cap; n++) { br.refill(); dst[n] = (uint8_t)sym1(); br.service(); }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    return br.p == 0;
+}
 
 // returns 0 exhausted exactly, 1 over-read, 2 cap reached, 3 ExtraPadding
 __device__ __forceinline__ int huf_stream2(const uint8_t *__restrict__ tsym, const uint8_t *__restrict__ tnb, uint32_t mb,
@@ -350,8 +479,8 @@ __global__ void __launch_bounds__(32) k_huf(const BlockDesc *__restrict__ descs,
                 // fast path: the standard split -- streams 0..2 regenerate S bytes, stream 3 the rest
                 if (regen >= 3 * S) {
                     uint32_t cap = k < 3 ? S : regen - 3 * S;
-                    rc = huf_stream2(tsym, tnb, mb, s0 + off[k], off[k + 1] - off[k], dst + k * S, cap, cap, count);
-                    irregular = (rc != 0) || (count != cap);
+                    uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(smem_huf + HUF_BLOCKS_PER_CTA * HUF_SMEM_PER_BLOCK + lane * RING_STRIDE);
+                    irregular = !huf_stream_fast(tsym, tnb, mb, s0 + off[k], off[k + 1] - off[k], dst + k * S, cap, ring_addr);
                 } else irregular = true;
                 // any anomaly in the group -> lane 0 of the group replays the block with the reference's exact semantics
                 uint32_t gmask = 0xFu << (lane & 28u);
@@ -430,10 +559,13 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
     uint32_t *s_ml_base = s_ll_base + 36;
     uint8_t *s_ll_bits = reinterpret_cast<uint8_t *>(s_ml_base + 53);
     uint8_t *s_ml_bits = s_ll_bits + 36;
+    uint32_t *s_ll = reinterpret_cast<uint32_t *>(smem_fse + FSE_BLOCKS_PER_CTA * FSE_TAB_U16 * 2 + 512);   // base | bits << 24
+    uint32_t *s_ml = s_ll + 36;
+    uint8_t *s_ring = smem_fse + FSE_BLOCKS_PER_CTA * FSE_TAB_U16 * 2 + 1024;                                // 32 x RING_STRIDE
     const uint32_t lane = threadIdx.x;
     const uint32_t b = blockIdx.x * FSE_BLOCKS_PER_CTA + lane;
-    for (uint32_t i = lane; i < 36; i += 32) { s_ll_base[i] = c_ll_base[i]; s_ll_bits[i] = c_ll_bits[i]; }
-    for (uint32_t i = lane; i < 53; i += 32) { s_ml_base[i] = c_ml_base[i]; s_ml_bits[i] = c_ml_bits[i]; }
+    for (uint32_t i = lane; i < 36; i += 32) { s_ll_base[i] = c_ll_base[i]; s_ll_bits[i] = c_ll_bits[i]; s_ll[i] = c_ll_base[i] | ((uint32_t)c_ll_bits[i] << 24); }
+    for (uint32_t i = lane; i < 53; i += 32) { s_ml_base[i] = c_ml_base[i]; s_ml_bits[i] = c_ml_bits[i]; s_ml[i] = c_ml_base[i] | ((uint32_t)c_ml_bits[i] << 24); }
 
     const bool active = b < nblocks;
     const BlockDesc *d = active ? &descs[b] : nullptr;
@@ -469,6 +601,97 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
     if (!active) return;
     if (!run) { aux[b].pad = st_seq; return; }
 
+    // ---------------- fast path: branch-free steps; anything unusual (bad code, > 32 extra bits in one sequence,
+    // under/over-run, uninitialised table) sets `bad` and the block is decoded again by the exact path below.
+    {
+        const uint8_t *src = input + d->src_off + aux[b].seq_bits_off;
+        const uint32_t len = d->src_size - aux[b].seq_bits_off;
+        const uint16_t *TL = tabs + lane * FSE_TAB_U16, *TM = TL + 512, *TO = TL + 1024;
+        RingBits br;
+        uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(s_ring + lane * RING_STRIDE);
+        bool bad = !br.init(src, len, ring_addr) || !tl || !tl->valid || !to || !to->valid || !tm || !tm->valid;
+        if (!bad) {
+            const uint32_t logL = tl->log, logM = tm->log, logO = to->log;
+            uint32_t eL, eM, eO;
+            br.refill(); eL = TL[shr_c(br.hi, 32u - logL)]; br.skip(logL);
+            br.refill(); eO = TO[shr_c(br.hi, 32u - logO)]; br.skip(logO);
+            br.refill(); eM = TM[shr_c(br.hi, 32u - logM)]; br.skip(logM);
+            uint32_t *out = seq_scratch + d->seq_buf_off * 3;
+            const uint32_t nseq = d->nseq;
+            const bool resolve = d->fse_resolves != 0;
+            uint32_t h0 = d->init_hist[0], h1 = d->init_hist[1], h2 = d->init_hist[2];
+            uint64_t sum_ml = 0;
+            uint32_t flags = 0;
+            uint32_t stage[12];
+            auto step = [&](uint32_t &o_ll, uint32_t &o_ml, uint32_t &o_of, bool update) {
+                const uint32_t cL = eL >> 10, cM = eM >> 10, cO = eO >> 10;
+                const uint32_t vL = s_ll[cL < 36 ? cL : 0], vM = s_ml[cM < 53 ? cM : 0];   // base | extra_bits << 24
+                const uint32_t xL = vL >> 24, xM = vM >> 24, xO = cO;
+                flags |= (cO > 31u) | (cL > 35u) | (cM > 52u);
+                // state transitions out of the compact entries (b200z_types.h): nb = log - floor(log2 f), base = (f - 2^h) << nb
+                const uint32_t fL = eL & 1023u, fM = eM & 1023u, fO = eO & 1023u;
+                const uint32_t hL = 31u - (uint32_t)__clz((int)fL), hM = 31u - (uint32_t)__clz((int)fM), hO = 31u - (uint32_t)__clz((int)fO);
+                const uint32_t nbL = logL - hL, nbM = logM - hM, nbO = logO - hO;
+                const uint32_t bL = (fL ^ (1u << hL)) << nbL, bM = (fM ^ (1u << hM)) << nbM, bO = (fO ^ (1u << hO)) << nbO;
+                // extra bits: OF, ML, LL (get_bits_triple, sequence_section_decoder.rs:185)
+                br.refill();
+                const uint32_t xsum = xO + xM + xL;
+                flags |= (xsum > 32u) | ((int32_t)xsum > br.fill);
+                const uint32_t t0 = br.hi, t1 = shl_c(t0, xO), t2 = shl_c(t1, xM);
+                const uint32_t obits = shr_c(t0, 32u - xO), ml_add = shr_c(t1, 32u - xM), ll_add = shr_c(t2, 32u - xL);
+                br.skip(xsum > 32u ? 32u : xsum);
+                uint32_t offset = obits + (1u << (cO & 31u));
+                const uint32_t ll = (vL & 0xFFFFFFu) + ll_add, ml = (vM & 0xFFFFFFu) + ml_add;
+                sum_ml += ml;
+                if (resolve) {   // do_offset_history (sequence_execution.rs:59-118) with selects
+                    const uint32_t kk = offset > 3u ? 4u : offset - 1u + (ll == 0u ? 1u : 0u);
+                    const uint32_t h0m1 = h0 ? h0 - 1u : 0u;
+                    const uint32_t actual = kk == 0u ? h0 : (kk == 1u ? h1 : (kk == 2u ? h2 : (kk == 3u ? h0m1 : offset - 3u)));
+                    h2 = kk <= 1u ? h2 : h1;
+                    h1 = kk == 0u ? h1 : h0;
+                    h0 = actual;
+                    offset = actual;
+                }
+                o_ll = ll; o_ml = ml; o_of = offset;
+                if (update) {   // state updates LL, ML, OF (:198-207)
+                    br.refill();
+                    const uint32_t u0 = br.hi, u1 = shl_c(u0, nbL), u2 = shl_c(u1, nbM);
+                    const uint32_t aL = shr_c(u0, 32u - nbL), aM = shr_c(u1, 32u - nbM), aO = shr_c(u2, 32u - nbO);
+                    br.skip(nbL + nbM + nbO);
+                    eL = TL[bL + aL]; eM = TM[bM + aM]; eO = TO[bO + aO];
+                }
+                br.service();
+                flags |= (uint32_t)(br.p < 0);
+            };
+            uint32_t i = 0;
+            for (; i + 4 < nseq; i += 4) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) step(stage[3 * q], stage[3 * q + 1], stage[3 * q + 2], true);
+                uint4 *o4 = reinterpret_cast<uint4 *>(out + 3 * i);
+                o4[0] = make_uint4(stage[0], stage[1], stage[2], stage[3]);
+                o4[1] = make_uint4(stage[4], stage[5], stage[6], stage[7]);
+                o4[2] = make_uint4(stage[8], stage[9], stage[10], stage[11]);
+                if (flags) break;
+            }
+            if (!flags) {
+                for (; i < nseq; i++) {
+                    uint32_t ll, ml, of;
+                    step(ll, ml, of, i + 1 < nseq);
+                    out[3 * i] = ll; out[3 * i + 1] = ml; out[3 * i + 2] = of;
+                }
+            }
+            bad = flags != 0 || br.p != 0;
+            if (!bad) {
+                aux[b].pad = 0;
+                if (resolve) { aux[b].hist_after[0] = h0; aux[b].hist_after[1] = h1; aux[b].hist_after[2] = h2; }
+                uint64_t total = sum_ml + d->regen_size;
+                aux[b].out_size = (uint32_t)(total > 0xffffffffull ? 0xffffffffull : total);
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (!bad) return;
+    }
+    // ---------------- exact path (rare): the reference's control flow, one check at a time
     uint32_t err = 0;
     uint64_t sum_ml = 0, sum_ll = 0;
     uint32_t h0r = 0, h1r = 0, h2r = 0;
@@ -796,12 +1019,13 @@ int launch_predefined(FseSlot *predef, cudaStream_t s) {
     return (int)cudaGetLastError();
 }
 
-constexpr uint32_t kFseSmem = FSE_BLOCKS_PER_CTA * FSE_TAB_U16 * 2 + (36 + 53) * 4 + 96;
+constexpr uint32_t kHufSmem = HUF_BLOCKS_PER_CTA * HUF_SMEM_PER_BLOCK + 32 * RING_STRIDE;
+constexpr uint32_t kFseSmem = FSE_BLOCKS_PER_CTA * FSE_TAB_U16 * 2 + 1024 + 32 * RING_STRIDE;
 
 int init_kernels() {
     cudaError_t e = cudaFuncSetAttribute(k_fse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFseSmem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_huf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HUF_BLOCKS_PER_CTA * HUF_SMEM_PER_BLOCK));
+    e = cudaFuncSetAttribute(k_huf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHufSmem);
     return (int)e;
 }
 
@@ -813,7 +1037,7 @@ int launch_stage(const PipelineArgs &a, int stage, cudaStream_t s) {
         case 0: if (a.nblocks) k_setup<<<cdiv(a.nblocks, SETUP_WARPS), SETUP_WARPS * 32, 0, s>>>(a.descs, a.aux, a.input, a.nblocks); break;
         case 1:
             if (a.nblocks)
-                k_huf<<<cdiv(a.nblocks, HUF_BLOCKS_PER_CTA), 32, HUF_BLOCKS_PER_CTA * HUF_SMEM_PER_BLOCK, s>>>(a.descs, a.aux, a.input, a.lit_scratch, a.nblocks);
+                k_huf<<<cdiv(a.nblocks, HUF_BLOCKS_PER_CTA), 32, kHufSmem, s>>>(a.descs, a.aux, a.input, a.lit_scratch, a.nblocks);
             break;
         case 2:
             if (a.nblocks)
