@@ -901,10 +901,14 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const BlockDesc *__res
             const bool resolved = d.fse_resolves != 0;
             const uint32_t *seqs = seq_scratch + d.seq_buf_off * 3;
             __syncwarp();
+            // sequence records are prefetched one batch ahead (they stream from HBM exactly once)
+            uint32_t nx_ll = 0, nx_ml = 0, nx_of = 1;
+            if (lane < d.nseq) { const uint32_t *s = seqs + (uint64_t)lane * 3; nx_ll = __ldg(s); nx_ml = __ldg(s + 1); nx_of = __ldg(s + 2); }
             for (uint32_t base = 0; base < d.nseq && !e; base += 32) {
                 const uint32_t nb = d.nseq - base < 32 ? d.nseq - base : 32;
-                uint32_t my_ll = 0, my_ml = 0, my_of = 1;
-                if (lane < nb) { const uint32_t *s = seqs + (uint64_t)(base + lane) * 3; my_ll = s[0]; my_ml = s[1]; my_of = s[2]; }
+                const uint32_t my_ll = nx_ll, my_ml = nx_ml, my_of = nx_of;
+                nx_ll = 0; nx_ml = 0; nx_of = 1;
+                if (base + 32 + lane < d.nseq) { const uint32_t *s = seqs + (uint64_t)(base + 32 + lane) * 3; nx_ll = __ldg(s); nx_ml = __ldg(s + 1); nx_of = __ldg(s + 2); }
                 // inclusive scans of ll and ll + ml
                 uint32_t lit_end = my_ll, out_end = my_ll + my_ml;
 #pragma unroll
@@ -951,38 +955,60 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const BlockDesc *__res
                 __syncwarp();
                 uint8_t *bout = out + st.produced;
                 uint32_t before = 0;   // match starts in earlier rows
-                for (uint32_t r = 0; r < nrows; r++) {
-                    const uint32_t q = (r << 5) + lane;
-                    const uint32_t word = mask[r];
-                    const uint32_t jm = before + __popc(word & le);   // match starts at or before q
-                    before += __popc(word);
-                    const uint32_t c = jm ? jm - 1 : 0;
-                    const uint32_t pk = __shfl_sync(0xffffffffu, pack, c);
-                    const uint32_t off = __shfl_sync(0xffffffffu, my_off, c);
-                    const uint32_t ls = __shfl_sync(0xffffffffu, l_start, jm & 31u);
-                    const bool valid = q < T;
-                    const uint32_t mend = pk >> 16, mst = pk & 0xffffu;
-                    const bool is_match = valid && jm && q < mend;
-                    if (valid && !is_match) {
-                        // literal run of sequence jm starts where match jm-1 ended (or at the batch start)
-                        uint32_t li = ls + (q - (jm ? mend : 0u));
-                        bout[q] = lit.rle ? lit.byte : lit.p[li];
-                    }
-                    uint32_t pending = __ballot_sync(0xffffffffu, is_match);
-                    if (pending) {
-                        uint32_t kk = q - mst;
-                        if (is_match && kk >= off) kk %= off;
-                        // source position relative to the batch start (may be negative: earlier output)
-                        const int32_t sp = (int32_t)mst - (int32_t)off + (int32_t)kk;
-                        const int32_t row0 = (int32_t)(r << 5);
-                        bool mine = is_match;
-                        while (pending) {
-                            __syncwarp();
-                            bool ready = mine && (sp < row0 || !((pending >> (sp - row0)) & 1u));
-                            if (ready) { bout[q] = bout[sp]; mine = false; }
-                            pending &= ~__ballot_sync(0xffffffffu, ready);
+                // rows are produced four at a time: every byte whose source lies before the chunk (literals, and
+                // matches reaching back past the chunk start) is loaded first -- up to 4 independent loads per lane
+                // in flight -- then stored; the few bytes whose source lies inside the chunk follow, row by row.
+                for (uint32_t r0 = 0; r0 < nrows; r0 += 4) {
+                    const int32_t chunk0 = (int32_t)(r0 << 5);
+                    uint32_t val[4]; int32_t spv[4]; uint32_t kind[4];   // kind: 0 none, 1 stored in phase 1, 2 dependent match
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint32_t r = r0 + i;
+                        const uint32_t q = (r << 5) + lane;
+                        const uint32_t word = r < nrows ? mask[r] : 0u;
+                        const uint32_t jm = before + __popc(word & le);   // match starts at or before q
+                        before += __popc(word);
+                        const uint32_t c = jm ? jm - 1 : 0;
+                        const uint32_t pk = __shfl_sync(0xffffffffu, pack, c);
+                        const uint32_t off = __shfl_sync(0xffffffffu, my_off, c);
+                        const uint32_t ls = __shfl_sync(0xffffffffu, l_start, jm & 31u);
+                        const bool valid = q < T;
+                        const uint32_t mend = pk >> 16, mst = pk & 0xffffu;
+                        const bool is_match = valid && jm && q < mend;
+                        kind[i] = 0; val[i] = 0; spv[i] = 0;
+                        if (valid && !is_match) {
+                            // literal run of sequence jm starts where match jm-1 ended (or at the batch start)
+                            const uint32_t li = ls + (q - (jm ? mend : 0u));
+                            val[i] = lit.rle ? lit.byte : lit.p[li];
+                            kind[i] = 1;
+                        } else if (is_match) {
+                            uint32_t kk = q - mst;
+                            if (kk >= off) kk %= off;
+                            const int32_t sp = (int32_t)mst - (int32_t)off + (int32_t)kk;   // batch-relative source
+                            spv[i] = sp;
+                            if (sp < chunk0) { val[i] = bout[sp]; kind[i] = 1; } else kind[i] = 2;
                         }
                     }
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if (kind[i] == 1) bout[((r0 + i) << 5) + lane] = (uint8_t)val[i];
+                    // dependent bytes (source inside this chunk), rows in order
+                    uint32_t anydep = __ballot_sync(0xffffffffu, kind[0] == 2 || kind[1] == 2 || kind[2] == 2 || kind[3] == 2);
+                    if (anydep) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            uint32_t pending = __ballot_sync(0xffffffffu, kind[i] == 2);
+                            const int32_t row0 = chunk0 + (i << 5);
+                            bool mine = kind[i] == 2;
+                            while (pending) {
+                                __syncwarp();
+                                bool ready = mine && (spv[i] < row0 || !((pending >> (spv[i] - row0)) & 1u));
+                                if (ready) { bout[row0 + (int32_t)lane] = bout[spv[i]]; mine = false; }
+                                pending &= ~__ballot_sync(0xffffffffu, ready);
+                            }
+                        }
+                    }
+                    __syncwarp();
                 }
                 __syncwarp();
                 st.produced += T; st.counter += T; st.litpos += L;
