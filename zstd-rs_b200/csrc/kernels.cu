@@ -239,7 +239,7 @@ struct RingBits {
         hi |= shr_c(w, (uint32_t)fill);
         lo |= shl_c(w, 32u - (uint32_t)fill);
         fill += need ? 32 : 0;
-        wi -= (need && wi > 0) ? 1 : 0;
+        wi -= need ? 1 : 0;                       // may run below zero: word() returns 0 there
         nextw = need ? word(wi - 1) : nextw;
     }
     // keeps the ring 7 groups ahead; call at least once per 4 consumed words (once per sequence / per 4 symbols)
@@ -625,9 +625,9 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
             uint32_t stage[12];
             auto step = [&](uint32_t &o_ll, uint32_t &o_ml, uint32_t &o_of, bool update) {
                 const uint32_t cL = eL >> 10, cM = eM >> 10, cO = eO >> 10;
-                const uint32_t vL = s_ll[cL < 36 ? cL : 0], vM = s_ml[cM < 53 ? cM : 0];   // base | extra_bits << 24
+                const uint32_t vL = s_ll[cL], vM = s_ml[cM];   // base | extra_bits << 24; codes are < 64 and the two LUTs are adjacent (89 entries + pad)
                 const uint32_t xL = vL >> 24, xM = vM >> 24, xO = cO;
-                flags |= (cO > 31u) | (cL > 35u) | (cM > 52u);
+                flags |= (cO >> 5);   // offset code > 31 (LL/ML codes are capped by table construction, scratch.rs:36-40)
                 // state transitions out of the compact entries (b200z_types.h): nb = log - floor(log2 f), base = (f - 2^h) << nb
                 const uint32_t fL = eL & 1023u, fM = eM & 1023u, fO = eO & 1023u;
                 const uint32_t hL = 31u - (uint32_t)__clz((int)fL), hM = 31u - (uint32_t)__clz((int)fM), hO = 31u - (uint32_t)__clz((int)fO);
@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
                 // extra bits: OF, ML, LL (get_bits_triple, sequence_section_decoder.rs:185)
                 br.refill();
                 const uint32_t xsum = xO + xM + xL;
-                flags |= (xsum > 32u) | ((int32_t)xsum > br.fill);
+                flags |= (xsum > 32u);
                 const uint32_t t0 = br.hi, t1 = shl_c(t0, xO), t2 = shl_c(t1, xM);
                 const uint32_t obits = shr_c(t0, 32u - xO), ml_add = shr_c(t1, 32u - xM), ll_add = shr_c(t2, 32u - xL);
                 br.skip(xsum > 32u ? 32u : xsum);
@@ -660,13 +660,12 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
                     br.skip(nbL + nbM + nbO);
                     eL = TL[bL + aL]; eM = TM[bM + aM]; eO = TO[bO + aO];
                 }
-                br.service();
-                flags |= (uint32_t)(br.p < 0);
             };
             uint32_t i = 0;
             for (; i + 4 < nseq; i += 4) {
 #pragma unroll
-                for (int q = 0; q < 4; q++) step(stage[3 * q], stage[3 * q + 1], stage[3 * q + 2], true);
+                for (int q = 0; q < 4; q++) { step(stage[3 * q], stage[3 * q + 1], stage[3 * q + 2], true); if (q & 1) br.service(); }
+                flags |= (uint32_t)(br.p < 0);   // bits_remaining only decreases: one check per group is equivalent
                 uint4 *o4 = reinterpret_cast<uint4 *>(out + 3 * i);
                 o4[0] = make_uint4(stage[0], stage[1], stage[2], stage[3]);
                 o4[1] = make_uint4(stage[4], stage[5], stage[6], stage[7]);
@@ -677,6 +676,8 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
                 for (; i < nseq; i++) {
                     uint32_t ll, ml, of;
                     step(ll, ml, of, i + 1 < nseq);
+                    br.service();
+                    flags |= (uint32_t)(br.p < 0);
                     out[3 * i] = ll; out[3 * i + 1] = ml; out[3 * i + 2] = of;
                 }
             }
@@ -846,9 +847,9 @@ __device__ uint32_t exec_batch_exact(ExecState &st, const LitSrc &lit, const Fra
 
 constexpr uint32_t EXEC_WARPS = 4;
 constexpr uint32_t EXEC_MAX_RUN = 127;                      // longest literal run / match the fast path takes
-constexpr uint32_t EXEC_MASK_WORDS = (32 * 2 * EXEC_MAX_RUN + 31) / 32 + 1;
+constexpr uint32_t EXEC_MASK_WORDS = (32 * 2 * EXEC_MAX_RUN + 31) / 32 + 4;
 
-__global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const BlockDesc *__restrict__ descs, const BlockAux *__restrict__ aux,
+__global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__restrict__ descs, const BlockAux *__restrict__ aux,
                                                         const FrameDesc *__restrict__ frames, FrameState *__restrict__ states,
                                                         const uint8_t *__restrict__ input, const uint8_t *__restrict__ lit_scratch,
                                                         const uint32_t *__restrict__ seq_scratch, uint8_t *__restrict__ output, uint64_t output_cap,
@@ -932,13 +933,13 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const BlockDesc *__res
                     uint32_t m_start = out_end - my_ml;
                     bool ok = lane >= nb || (my_ll <= EXEC_MAX_RUN && my_ml <= EXEC_MAX_RUN && my_off != 0 &&
                                              (uint64_t)my_off <= st.produced - st.drained + m_start);
-                    fast = __all_sync(0xffffffffu, ok) && (uint64_t)st.litpos + L <= lit.regen && st.produced + T <= st.cap;
+                    fast = __all_sync(0xffffffffu, ok) && (uint64_t)st.litpos + L <= lit.regen && st.produced + T <= st.cap && !lit.rle;
                     if (fast) { st.h0 = h0; st.h1 = h1; st.h2 = h2; }
                 } else {
                     uint32_t m_start = out_end - my_ml;
                     bool ok = lane >= nb || (my_ll <= EXEC_MAX_RUN && my_ml <= EXEC_MAX_RUN && my_off != 0 &&
                                              (uint64_t)my_off <= st.produced - st.drained + m_start);
-                    fast = __all_sync(0xffffffffu, ok) && (uint64_t)st.litpos + L <= lit.regen && st.produced + T <= st.cap;
+                    fast = __all_sync(0xffffffffu, ok) && (uint64_t)st.litpos + L <= lit.regen && st.produced + T <= st.cap && !lit.rle;
                 }
                 if (!fast) {
                     e = exec_batch_exact(st, lit, fd, out, nb, my_ll, my_ml, my_of, resolved, lane);
@@ -949,7 +950,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const BlockDesc *__res
                 const uint32_t pack = m_start | (out_end << 16);       // T <= 8128 < 2^16
                 const uint32_t l_start = st.litpos + lit_end - my_ll;  // literal index of my literal run
                 const uint32_t nrows = (T + 31) >> 5;
-                for (uint32_t w = lane; w < nrows; w += 32) mask[w] = 0;
+                for (uint32_t w = lane; w < ((nrows + 3u) & ~3u); w += 32) mask[w] = 0;
                 __syncwarp();
                 if (lane < nb) atomicOr(&mask[m_start >> 5], 1u << (m_start & 31u));
                 __syncwarp();
@@ -960,46 +961,44 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const BlockDesc *__res
                 // in flight -- then stored; the few bytes whose source lies inside the chunk follow, row by row.
                 for (uint32_t r0 = 0; r0 < nrows; r0 += 4) {
                     const int32_t chunk0 = (int32_t)(r0 << 5);
-                    uint32_t val[4]; int32_t spv[4]; uint32_t kind[4];   // kind: 0 none, 1 stored in phase 1, 2 dependent match
+                    uint32_t val[4]; int32_t spv[4]; bool indep[4], dep[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         const uint32_t r = r0 + i;
                         const uint32_t q = (r << 5) + lane;
-                        const uint32_t word = r < nrows ? mask[r] : 0u;
-                        const uint32_t jm = before + __popc(word & le);   // match starts at or before q
+                        const uint32_t word = mask[r];                      // words up to the next multiple of 4 rows are zeroed
+                        const uint32_t jm = before + __popc(word & le);     // match starts at or before q
                         before += __popc(word);
-                        const uint32_t c = jm ? jm - 1 : 0;
+                        const uint32_t c = max(jm, 1u) - 1u;
                         const uint32_t pk = __shfl_sync(0xffffffffu, pack, c);
                         const uint32_t off = __shfl_sync(0xffffffffu, my_off, c);
                         const uint32_t ls = __shfl_sync(0xffffffffu, l_start, jm & 31u);
-                        const bool valid = q < T;
                         const uint32_t mend = pk >> 16, mst = pk & 0xffffu;
-                        const bool is_match = valid && jm && q < mend;
-                        kind[i] = 0; val[i] = 0; spv[i] = 0;
-                        if (valid && !is_match) {
-                            // literal run of sequence jm starts where match jm-1 ended (or at the batch start)
-                            const uint32_t li = ls + (q - (jm ? mend : 0u));
-                            val[i] = lit.rle ? lit.byte : lit.p[li];
-                            kind[i] = 1;
-                        } else if (is_match) {
-                            uint32_t kk = q - mst;
-                            if (kk >= off) kk %= off;
-                            const int32_t sp = (int32_t)mst - (int32_t)off + (int32_t)kk;   // batch-relative source
-                            spv[i] = sp;
-                            if (sp < chunk0) { val[i] = bout[sp]; kind[i] = 1; } else kind[i] = 2;
-                        }
+                        const bool valid = q < T;
+                        const bool is_match = valid & (jm != 0u) & (q < mend);
+                        // literal run of sequence jm starts where match jm-1 ended (or at the batch start)
+                        const uint32_t li = ls + q - (jm ? mend : 0u);
+                        uint32_t kk = q - mst;
+                        const bool ovl = is_match & (kk >= off);
+                        if (__any_sync(0xffffffffu, ovl)) { if (ovl) kk %= off; }   // overlapping match: byte k comes from k mod offset
+                        const int32_t sp = (int32_t)mst - (int32_t)off + (int32_t)kk;  // batch-relative source of a match byte
+                        spv[i] = sp;
+                        indep[i] = is_match ? (sp < chunk0) : valid;
+                        dep[i] = is_match & !(sp < chunk0);
+                        const uint8_t *ptr = is_match ? (const uint8_t *)(bout + sp) : lit.p + li;
+                        val[i] = 0;
+                        if (indep[i]) val[i] = *ptr;
                     }
 #pragma unroll
                     for (int i = 0; i < 4; i++)
-                        if (kind[i] == 1) bout[((r0 + i) << 5) + lane] = (uint8_t)val[i];
+                        if (indep[i]) bout[((r0 + i) << 5) + lane] = (uint8_t)val[i];
                     // dependent bytes (source inside this chunk), rows in order
-                    uint32_t anydep = __ballot_sync(0xffffffffu, kind[0] == 2 || kind[1] == 2 || kind[2] == 2 || kind[3] == 2);
-                    if (anydep) {
+                    if (__any_sync(0xffffffffu, dep[0] | dep[1] | dep[2] | dep[3])) {
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
-                            uint32_t pending = __ballot_sync(0xffffffffu, kind[i] == 2);
+                            uint32_t pending = __ballot_sync(0xffffffffu, dep[i]);
                             const int32_t row0 = chunk0 + (i << 5);
-                            bool mine = kind[i] == 2;
+                            bool mine = dep[i];
                             while (pending) {
                                 __syncwarp();
                                 bool ready = mine && (spv[i] < row0 || !((pending >> (spv[i] - row0)) & 1u));
