@@ -327,6 +327,25 @@ def test_synthetic_configs_small(pkg, ctx, oracle):
         assert np.array_equal(o_out[:fs.D], out[:fs.D]) and (o_sz == fs.out_size).all()
 
 
+def test_pipelined_one_shot_many_chunks(pkg, ctx, monkeypatch):
+    """The host-to-host one-shot call overlaps planning / PCIe / kernels over several chunks of frames; force tiny chunks."""
+    import datagen as G
+    monkeypatch.setenv("B200Z_PIPELINE_CHUNK_BYTES", str(1 << 20))
+    fs = G.config_c3(nframes=200, cache=False)
+    out = np.zeros(fs.D + 16, dtype=np.uint8)
+    res = pkg.decode_frames(ctx, fs.comp, fs.frames_io(), out)
+    assert (res["status"] == 0).all() and (res["out_size"] == fs.out_size).all()
+    assert np.array_equal(out[:fs.D], fs.plain)
+    assert (res["bytes_read"] == fs.src_size).all() and (res["has_checksum"] == 1).all()
+    # a broken frame in the middle fails alone
+    comp = fs.comp.copy()
+    comp[int(fs.src_off[77]) + 12] ^= 0xFF
+    res = pkg.decode_frames(ctx, comp, fs.frames_io(), out)
+    assert res[77]["status"] != 0 or not np.array_equal(out[fs.out_off[77]:fs.out_off[77] + fs.out_size[77]], fs.plain[fs.out_off[77]:fs.out_off[77] + fs.out_size[77]])
+    ok = np.ones(fs.nframes, bool); ok[77] = False
+    assert (res["status"][ok] == 0).all()
+
+
 def test_target_too_small_and_capacity_isolation(pkg, ctx):
     """A frame that does not fit its out_cap fails alone and never writes past its slot (checked on the device buffer)."""
     import torch

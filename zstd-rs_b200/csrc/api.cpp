@@ -3,6 +3,7 @@
 // There is no CPU decode path in this library: without a usable CUDA device b200z_ctx_create fails.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -78,6 +79,9 @@ struct DevBuf {
 struct b200z_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;          // k_huf runs here, beside k_fse
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    struct PipeResources *pipe = nullptr;  // lazily created by the pipelined one-shot path
     FseSlot *d_predef = nullptr;
     std::string err;
     uint64_t launches = 0;
@@ -108,6 +112,8 @@ extern "C" int b200z_ctx_create(int device, b200z_ctx **out) {
     c->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return B200Z_ERR_NO_DEVICE; }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return B200Z_ERR_NO_DEVICE; }
+    if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return B200Z_ERR_CUDA; }
     if (cudaMalloc((void **)&c->d_predef, sizeof(FseSlot)) != cudaSuccess) { cudaGetLastError(); return B200Z_ERR_OUT_OF_MEMORY; }
     if (init_kernels()) { cudaGetLastError(); return B200Z_ERR_CUDA; }
     int e = launch_predefined(c->d_predef, c->stream);
@@ -116,10 +122,15 @@ extern "C" int b200z_ctx_create(int device, b200z_ctx **out) {
     *out = c.release();
     return 0;
 }
+static void pipe_free(b200z_ctx *c);
 extern "C" void b200z_ctx_destroy(b200z_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    pipe_free(c);
     if (c->d_predef) cudaFree(c->d_predef);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->side) cudaStreamDestroy(c->side);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -238,7 +249,8 @@ struct Submission {
         n_huf = n_fse = 0; lit_bytes = 0; nseq = 0;
     }
     // resolve table references to device pointers and upload descriptors
-    int upload(b200z_ctx *c) {
+    int upload(b200z_ctx *c, cudaStream_t stream = nullptr) {
+        if (!stream) stream = c->stream;
         int e;
         if ((e = d_descs.ensure(descs.size() * sizeof(BlockDesc)))) return e;
         if ((e = d_aux.ensure(descs.size() * sizeof(BlockAux)))) return e;
@@ -270,9 +282,9 @@ struct Submission {
             d.ll = fse(r.ll, 0); d.of = fse(r.of, 1); d.ml = fse(r.ml, 2);
             d.fse_build = r.build_fse >= 0 ? fs + r.build_fse : nullptr;
         }
-        if (!descs.empty()) CU(c, cudaMemcpyAsync(d_descs.p, descs.data(), descs.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice, c->stream));
-        if (!frames.empty()) CU(c, cudaMemcpyAsync(d_frames.p, frames.data(), frames.size() * sizeof(FrameDesc), cudaMemcpyHostToDevice, c->stream));
-        if (!states.empty()) CU(c, cudaMemcpyAsync(d_states.p, states.data(), states.size() * sizeof(FrameState), cudaMemcpyHostToDevice, c->stream));
+        if (!descs.empty()) CU(c, cudaMemcpyAsync(d_descs.p, descs.data(), descs.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice, stream));
+        if (!frames.empty()) CU(c, cudaMemcpyAsync(d_frames.p, frames.data(), frames.size() * sizeof(FrameDesc), cudaMemcpyHostToDevice, stream));
+        if (!states.empty()) CU(c, cudaMemcpyAsync(d_states.p, states.data(), states.size() * sizeof(FrameState), cudaMemcpyHostToDevice, stream));
         return 0;
     }
     PipelineArgs args(const uint8_t *d_input, uint8_t *d_output, uint64_t out_cap) const {
@@ -455,7 +467,8 @@ extern "C" int b200z_batch_run(b200z_batch *b, uint8_t *d_output, size_t output_
     if (!s.states.empty())
         CU(c, cudaMemcpyAsync(s.d_states.p, b->d_states_init.p, s.states.size() * sizeof(FrameState), cudaMemcpyDeviceToDevice, c->stream));
     PipelineArgs a = s.args(b->d_input, d_output, output_cap);
-    int e = launch_pipeline(a, c->stream);
+    PipelineStreams ps{c->stream, c->side, c->ev_fork, c->ev_join};
+    int e = launch_pipeline_overlapped(a, ps);
     if (e) return c->set_cuda_err((cudaError_t)e, "launch_pipeline");
     c->launches += pipeline_launch_count(a);
     b->ran = true;
@@ -568,10 +581,147 @@ extern "C" void b200z_batch_destroy(b200z_batch *b) {
     delete b;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Pipelined one-shot for HOST buffers: the frame list is cut into a few chunks; while chunk i is being decoded,
+// chunk i+1 is planned on the host and its input crosses PCIe, and chunk i-1's plaintext is on its way back.
+// Three streams (H2D, compute, D2H) + two descriptor/scratch sets; all device buffers live in the context and are
+// reused across calls.
+// ---------------------------------------------------------------------------------------------------------------
+struct PipeResources {
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    b200z_batch *set[2] = {nullptr, nullptr};
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    FrameState *h_states[2] = {nullptr, nullptr};   // pinned
+    size_t h_states_cap[2] = {0, 0};
+    DevBuf d_in[2];
+    DevBuf d_out;
+};
+
+static void pipe_free(b200z_ctx *c) {
+    PipeResources *p = c->pipe;
+    if (!p) return;
+    for (int i = 0; i < 2; i++) {
+        if (p->set[i]) delete p->set[i];
+        if (p->ev_h2d[i]) cudaEventDestroy(p->ev_h2d[i]);
+        if (p->ev_k[i]) cudaEventDestroy(p->ev_k[i]);
+        if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]);
+        if (p->h_states[i]) cudaFreeHost(p->h_states[i]);
+    }
+    if (p->s_h2d) cudaStreamDestroy(p->s_h2d);
+    if (p->s_d2h) cudaStreamDestroy(p->s_d2h);
+    delete p;
+    c->pipe = nullptr;
+}
+
+static int pipe_get(b200z_ctx *c, PipeResources **out) {
+    if (!c->pipe) {
+        std::unique_ptr<PipeResources> p(new PipeResources());
+        CU(c, cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
+        CU(c, cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            p->set[i] = new b200z_batch();
+            p->set[i]->ctx = c;
+            CU(c, cudaEventCreateWithFlags(&p->ev_h2d[i], cudaEventDisableTiming));
+            CU(c, cudaEventCreateWithFlags(&p->ev_k[i], cudaEventDisableTiming));
+            CU(c, cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming));
+        }
+        c->pipe = p.release();
+    }
+    *out = c->pipe;
+    return 0;
+}
+
+static int decode_frames_pipelined(b200z_ctx *c, const uint8_t *input, size_t input_len, const b200z_frame_io *frames, size_t nframes,
+                                   const b200z_dict *const *dicts, size_t ndicts, const b200z_dict *forced, uint64_t max_window, uint8_t *output,
+                                   size_t output_cap, b200z_frame_result *results, size_t nchunks) {
+    PipeResources *p = nullptr;
+    if (int e = pipe_get(c, &p)) return e;
+    if (int e = p->d_out.ensure(output_cap + 64, false)) return e;
+    uint8_t *d_out = p->d_out.as<uint8_t>();
+    // chunk boundaries: consecutive frames, roughly equal output bytes
+    uint64_t total_cap = 0;
+    for (size_t i = 0; i < nframes; i++) total_cap += frames[i].out_cap;
+    std::vector<size_t> cut(1, 0);
+    {
+        uint64_t acc = 0, per = total_cap / nchunks + 1;
+        for (size_t i = 0; i < nframes; i++) {
+            acc += frames[i].out_cap;
+            if (acc >= per * cut.size() && i + 1 < nframes && cut.size() < nchunks) cut.push_back(i + 1);
+        }
+        cut.push_back(nframes);
+    }
+    struct Pending { size_t f0 = 0, f1 = 0; bool live = false; } pend[2];
+    auto retire = [&](int s) -> int {   // results of the chunk that used set s
+        if (!pend[s].live) return 0;
+        CU(c, cudaEventSynchronize(p->ev_done[s]));
+        b200z_batch *b = p->set[s];
+        for (size_t i = pend[s].f0; i < pend[s].f1; i++) {
+            int32_t sf = b->info[i - pend[s].f0].sub_frame;
+            fill_result(b, i - pend[s].f0, sf >= 0 ? &p->h_states[s][sf] : nullptr, results[i]);
+        }
+        pend[s].live = false;
+        return 0;
+    };
+    for (size_t ci = 0; ci + 1 < cut.size(); ci++) {
+        const int s = (int)(ci & 1);
+        const size_t f0 = cut[ci], f1 = cut[ci + 1];
+        if (int e = retire(s)) return e;
+        b200z_batch *b = p->set[s];
+        if (int e = plan_batch(b, input, input_len, frames + f0, f1 - f0, dicts, ndicts, forced, max_window)) return e;
+        // input byte range and output byte range of this chunk
+        uint64_t ilo = UINT64_MAX, ihi = 0, olo = UINT64_MAX, ohi = 0;
+        for (size_t i = f0; i < f1; i++) {
+            if (frames[i].src_off > input_len || frames[i].src_size > input_len - frames[i].src_off) continue;
+            ilo = std::min<uint64_t>(ilo, frames[i].src_off); ihi = std::max<uint64_t>(ihi, frames[i].src_off + frames[i].src_size);
+            if (frames[i].out_cap) { olo = std::min<uint64_t>(olo, frames[i].out_off); ohi = std::max<uint64_t>(ohi, frames[i].out_off + frames[i].out_cap); }
+        }
+        if (ihi < ilo) { ilo = ihi = 0; }
+        if (ohi < olo) { olo = ohi = 0; }
+        ohi = std::min<uint64_t>(ohi, output_cap); olo = std::min<uint64_t>(olo, ohi);
+        if (int e = p->d_in[s].ensure(ihi - ilo + 32)) return e;
+        if (ihi > ilo) CU(c, cudaMemcpyAsync(p->d_in[s].p, input + ilo, ihi - ilo, cudaMemcpyHostToDevice, p->s_h2d));
+        if (int e = b->sub.upload(c, p->s_h2d)) return e;
+        CU(c, cudaEventRecord(p->ev_h2d[s], p->s_h2d));
+        CU(c, cudaStreamWaitEvent(c->stream, p->ev_h2d[s], 0));
+        PipelineArgs a = b->sub.args(p->d_in[s].as<uint8_t>() - ilo, d_out, output_cap);
+        PipelineStreams ps{c->stream, c->side, c->ev_fork, c->ev_join};
+        int le = launch_pipeline_overlapped(a, ps);
+        if (le) return c->set_cuda_err((cudaError_t)le, "launch_pipeline");
+        c->launches += pipeline_launch_count(a);
+        CU(c, cudaEventRecord(p->ev_k[s], c->stream));
+        CU(c, cudaStreamWaitEvent(p->s_d2h, p->ev_k[s], 0));
+        size_t nst = b->sub.states.size();
+        if (nst > p->h_states_cap[s]) {
+            if (p->h_states[s]) cudaFreeHost(p->h_states[s]);
+            p->h_states[s] = nullptr; p->h_states_cap[s] = 0;
+            CU(c, cudaMallocHost((void **)&p->h_states[s], (nst + nst / 2 + 16) * sizeof(FrameState)));
+            p->h_states_cap[s] = nst + nst / 2 + 16;
+        }
+        if (nst) CU(c, cudaMemcpyAsync(p->h_states[s], b->sub.d_states.p, nst * sizeof(FrameState), cudaMemcpyDeviceToHost, p->s_d2h));
+        if (ohi > olo) CU(c, cudaMemcpyAsync(output + olo, d_out + olo, ohi - olo, cudaMemcpyDeviceToHost, p->s_d2h));
+        CU(c, cudaEventRecord(p->ev_done[s], p->s_d2h));
+        pend[s].f0 = f0; pend[s].f1 = f1; pend[s].live = true;
+    }
+    if (int e = retire(0)) return e;
+    if (int e = retire(1)) return e;
+    return 0;
+}
+
 extern "C" int b200z_decode_frames_batch(b200z_ctx *c, const uint8_t *input, size_t input_len, int input_mem, const b200z_frame_io *frames,
                                          size_t nframes, const b200z_dict *const *dicts, size_t ndicts, const b200z_dict *forced,
                                          uint64_t max_window, uint8_t *output, size_t output_cap, int output_mem, b200z_frame_result *results) {
     if (!c || !results || (!output && output_cap)) return B200Z_ERR_INVALID_ARGUMENT;
+    if (input_mem != B200Z_MEM_DEVICE && output_mem != B200Z_MEM_DEVICE && nframes >= 64) {
+        // host in, host out: overlap planning, PCIe and kernels
+        if (int e0 = c->use()) return e0;
+        if ((!input && input_len) || (!frames && nframes) || (!dicts && ndicts)) return B200Z_ERR_INVALID_ARGUMENT;
+        uint64_t total_cap = 0;
+        for (size_t i = 0; i < nframes; i++) total_cap += frames[i].out_cap;
+        uint64_t chunk_bytes = 256ull << 20;   // ~4 chunks per GiB: PCIe transfers and kernels of neighbouring chunks overlap
+        if (const char *ev = getenv("B200Z_PIPELINE_CHUNK_BYTES")) { uint64_t v = strtoull(ev, nullptr, 10); if (v >= 4096) chunk_bytes = v; }
+        size_t nchunks = (size_t)std::min<uint64_t>(16, std::max<uint64_t>(1, total_cap / chunk_bytes));
+        return decode_frames_pipelined(c, input, input_len, frames, nframes, dicts, ndicts, forced, max_window, output, output_cap, results, nchunks);
+    }
     b200z_batch *b = nullptr;
     int e = b200z_batch_prepare(c, input, input_len, input_mem, frames, nframes, dicts, ndicts, forced, max_window, &b);
     if (e) return e;

@@ -961,44 +961,46 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
                 // in flight -- then stored; the few bytes whose source lies inside the chunk follow, row by row.
                 for (uint32_t r0 = 0; r0 < nrows; r0 += 4) {
                     const int32_t chunk0 = (int32_t)(r0 << 5);
-                    uint32_t val[4]; int32_t spv[4]; bool indep[4], dep[4];
+                    uint32_t val[4]; int32_t spv[4]; uint32_t kind[4];   // kind: 0 none, 1 stored in phase 1, 2 dependent match
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         const uint32_t r = r0 + i;
                         const uint32_t q = (r << 5) + lane;
-                        const uint32_t word = mask[r];                      // words up to the next multiple of 4 rows are zeroed
-                        const uint32_t jm = before + __popc(word & le);     // match starts at or before q
+                        const uint32_t word = r < nrows ? mask[r] : 0u;
+                        const uint32_t jm = before + __popc(word & le);   // match starts at or before q
                         before += __popc(word);
-                        const uint32_t c = max(jm, 1u) - 1u;
+                        const uint32_t c = jm ? jm - 1 : 0;
                         const uint32_t pk = __shfl_sync(0xffffffffu, pack, c);
                         const uint32_t off = __shfl_sync(0xffffffffu, my_off, c);
                         const uint32_t ls = __shfl_sync(0xffffffffu, l_start, jm & 31u);
-                        const uint32_t mend = pk >> 16, mst = pk & 0xffffu;
                         const bool valid = q < T;
-                        const bool is_match = valid & (jm != 0u) & (q < mend);
-                        // literal run of sequence jm starts where match jm-1 ended (or at the batch start)
-                        const uint32_t li = ls + q - (jm ? mend : 0u);
-                        uint32_t kk = q - mst;
-                        const bool ovl = is_match & (kk >= off);
-                        if (__any_sync(0xffffffffu, ovl)) { if (ovl) kk %= off; }   // overlapping match: byte k comes from k mod offset
-                        const int32_t sp = (int32_t)mst - (int32_t)off + (int32_t)kk;  // batch-relative source of a match byte
-                        spv[i] = sp;
-                        indep[i] = is_match ? (sp < chunk0) : valid;
-                        dep[i] = is_match & !(sp < chunk0);
-                        const uint8_t *ptr = is_match ? (const uint8_t *)(bout + sp) : lit.p + li;
-                        val[i] = 0;
-                        if (indep[i]) val[i] = *ptr;
+                        const uint32_t mend = pk >> 16, mst = pk & 0xffffu;
+                        const bool is_match = valid && jm && q < mend;
+                        kind[i] = 0; val[i] = 0; spv[i] = 0;
+                        if (valid && !is_match) {
+                            // literal run of sequence jm starts where match jm-1 ended (or at the batch start)
+                            const uint32_t li = ls + (q - (jm ? mend : 0u));
+                            val[i] = lit.rle ? lit.byte : lit.p[li];
+                            kind[i] = 1;
+                        } else if (is_match) {
+                            uint32_t kk = q - mst;
+                            if (kk >= off) kk %= off;
+                            const int32_t sp = (int32_t)mst - (int32_t)off + (int32_t)kk;   // batch-relative source
+                            spv[i] = sp;
+                            if (sp < chunk0) { val[i] = bout[sp]; kind[i] = 1; } else kind[i] = 2;
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < 4; i++)
-                        if (indep[i]) bout[((r0 + i) << 5) + lane] = (uint8_t)val[i];
+                        if (kind[i] == 1) bout[((r0 + i) << 5) + lane] = (uint8_t)val[i];
                     // dependent bytes (source inside this chunk), rows in order
-                    if (__any_sync(0xffffffffu, dep[0] | dep[1] | dep[2] | dep[3])) {
+                    uint32_t anydep = __ballot_sync(0xffffffffu, kind[0] == 2 || kind[1] == 2 || kind[2] == 2 || kind[3] == 2);
+                    if (anydep) {
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
-                            uint32_t pending = __ballot_sync(0xffffffffu, dep[i]);
+                            uint32_t pending = __ballot_sync(0xffffffffu, kind[i] == 2);
                             const int32_t row0 = chunk0 + (i << 5);
-                            bool mine = dep[i];
+                            bool mine = kind[i] == 2;
                             while (pending) {
                                 __syncwarp();
                                 bool ready = mine && (spv[i] < row0 || !((pending >> (spv[i] - row0)) & 1u));
@@ -1081,6 +1083,23 @@ int launch_stage(const PipelineArgs &a, int stage, cudaStream_t s) {
 int launch_pipeline(const PipelineArgs &a, cudaStream_t s) {
     for (int st = 0; st < kNumStages; st++) { int e = launch_stage(a, st, s); if (e) return e; }
     return 0;
+}
+
+// k_huf and k_fse are independent (literals vs sequences of the same blocks) and both leave most issue slots
+// idle (a few latency-bound warps per SM): run them side by side -- k_huf on the side stream, forked after
+// k_setup and joined before k_exec.
+int launch_pipeline_overlapped(const PipelineArgs &a, const PipelineStreams &ps) {
+    int e;
+    if ((e = launch_stage(a, 0, ps.main))) return e;
+    if (a.nblocks) {
+        if ((e = (int)cudaEventRecord(ps.fork, ps.main))) return e;
+        if ((e = (int)cudaStreamWaitEvent(ps.side, ps.fork, 0))) return e;
+        if ((e = launch_stage(a, 1, ps.side))) return e;
+        if ((e = (int)cudaEventRecord(ps.join, ps.side))) return e;
+        if ((e = launch_stage(a, 2, ps.main))) return e;
+        if ((e = (int)cudaStreamWaitEvent(ps.main, ps.join, 0))) return e;
+    }
+    return launch_stage(a, 3, ps.main);
 }
 
 uint32_t pipeline_launch_count(const PipelineArgs &a) { return (a.nblocks ? 3u : 0u) + (a.nframes ? 1u : 0u); }
