@@ -111,8 +111,10 @@ extern "C" int b200z_ctx_create(int device, b200z_ctx **out) {
     std::unique_ptr<b200z_ctx> c(new b200z_ctx());
     c->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return B200Z_ERR_NO_DEVICE; }
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return B200Z_ERR_NO_DEVICE; }
-    if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { cudaGetLastError(); return B200Z_ERR_NO_DEVICE; }
+    if (cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_lo) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return B200Z_ERR_CUDA; }
     if (cudaMalloc((void **)&c->d_predef, sizeof(FseSlot)) != cudaSuccess) { cudaGetLastError(); return B200Z_ERR_OUT_OF_MEMORY; }
     if (init_kernels()) { cudaGetLastError(); return B200Z_ERR_CUDA; }

@@ -21,7 +21,8 @@ enum : uint32_t { MODE_PREDEFINED = 0, MODE_RLE = 1, MODE_FSE = 2, MODE_REPEAT =
 
 constexpr uint32_t HUF_MAX_BITS = 11;         // huff0_decoder.rs:9
 constexpr uint32_t HUF_TABLE_ENTRIES = 2048;  // 1 << 11
-constexpr uint32_t FSE_MAX_ENTRIES = 512;     // LL/ML max log 9 (sequence_section_decoder.rs:288-292)
+constexpr uint32_t FSE_MAX_ENTRIES = 512;
+constexpr uint32_t FSE_PROGRESS_FINAL = 0xFFFFFFFFu;     // LL/ML max log 9 (sequence_section_decoder.rs:288-292)
 
 // huff0 LUT, split so that it costs 3 KiB of shared memory per block instead of 4 (occupancy: every block of a
 // 1 GiB submission is in flight at once): sym[i] = symbol, nb4[i >> 1] holds the 4-bit code length of entries
@@ -101,7 +102,9 @@ struct alignas(16) BlockAux {
     uint32_t sum_ll;         // sum of literal lengths over the block's sequences
     uint32_t pad;            // sequence-stage status (code | stage << 16); literals-stage status is `status`
     uint32_t hist_after[3];  // offset history after the block, when fse_resolves
-    uint32_t pad2[3];
+    uint32_t progress;       // sequences k_fse has published so far (FSE_PROGRESS_FINAL when the block's sequence stage is over);
+                             // k_exec runs beside k_fse and consumes sequences as they appear
+    uint32_t pad2[2];
 };
 
 // Per-frame state: carried between submissions for the streaming mirror, fresh for batch frames.

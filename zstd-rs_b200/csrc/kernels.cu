@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(const BlockDesc *__r
         BlockAux a;
         a.status = st_lit;   // literals-stage status; the sequence-stage status travels in `pad` until k_exec orders them
         a.out_size = 0; a.lit_streams_off = lit_streams_off; a.seq_bits_off = seq_bits_off; a.sum_ll = 0; a.pad = st_seq;
-        a.hist_after[0] = a.hist_after[1] = a.hist_after[2] = 0; a.pad2[0] = a.pad2[1] = a.pad2[2] = 0;
+        a.hist_after[0] = a.hist_after[1] = a.hist_after[2] = 0; a.progress = 0; a.pad2[0] = a.pad2[1] = 0;
         aux[b] = a;
     }
 }
@@ -539,6 +539,12 @@ __device__ __forceinline__ uint32_t offset_history_step(uint32_t of, uint32_t ll
     return actual;
 }
 
+// progress hand-off to k_exec (which runs concurrently): records first, fence, then the counter
+__device__ __forceinline__ void fse_publish(BlockAux *aux, uint32_t b, uint32_t nseq_done) {
+    __threadfence();
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(&aux[b].progress), "r"(nseq_done) : "memory");
+}
+
 struct FseState {
     uint32_t e;   // current 16-bit entry
     __device__ __forceinline__ uint32_t sym() const { return e >> 10; }
@@ -599,7 +605,7 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
     }
     __syncwarp();
     if (!active) return;
-    if (!run) { aux[b].pad = st_seq; return; }
+    if (!run) { aux[b].pad = st_seq; fse_publish(aux, b, FSE_PROGRESS_FINAL); return; }
 
     // ---------------- fast path: branch-free steps; anything unusual (bad code, > 32 extra bits in one sequence,
     // under/over-run, uninitialised table) sets `bad` and the block is decoded again by the exact path below.
@@ -671,6 +677,7 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
                 o4[1] = make_uint4(stage[4], stage[5], stage[6], stage[7]);
                 o4[2] = make_uint4(stage[8], stage[9], stage[10], stage[11]);
                 if (flags) break;
+                if (((i + 4) & 127u) == 0) fse_publish(aux, b, i + 4);   // every 128 sequences: the fence costs ~1 us
             }
             if (!flags) {
                 for (; i < nseq; i++) {
@@ -690,7 +697,7 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (!bad) return;
+        if (!bad) { fse_publish(aux, b, FSE_PROGRESS_FINAL); return; }
     }
     // ---------------- exact path (rare): the reference's control flow, one check at a time
     uint32_t err = 0;
@@ -766,6 +773,7 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
     aux[b].sum_ll = (uint32_t)(sum_ll > 0xffffffffull ? 0xffffffffull : sum_ll);
     uint64_t total = sum_ml + d->regen_size;
     aux[b].out_size = (uint32_t)(total > 0xffffffffull ? 0xffffffffull : total);
+    fse_publish(aux, b, FSE_PROGRESS_FINAL);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -845,6 +853,34 @@ __device__ uint32_t exec_batch_exact(ExecState &st, const LitSrc &lit, const Fra
     return 0;
 }
 
+// ---- hand-off from k_fse (see fse_publish).  Bounded polling: if the producer never shows up (it always does: k_fse is
+// launched first and fits on the device in one wave) the frame fails with an internal error instead of hanging the GPU.
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// waits until at least `need` sequences of block b are published (or the block is final); returns the published count,
+// 0xFFFFFFFE on timeout.  Warp-uniform.
+__device__ __forceinline__ uint32_t exec_wait_progress(const BlockAux *aux, uint32_t b, uint32_t need, uint32_t lane) {
+    uint32_t v = 0;
+    if (lane == 0) {
+        uint32_t spins = 0;
+        for (;;) {
+            v = ld_acquire_u32(&aux[b].progress);
+            if (v >= need) break;
+            __nanosleep(128);
+            if (++spins > (1u << 22)) { v = 0xFFFFFFFEu; break; }
+        }
+    }
+    return __shfl_sync(0xffffffffu, v, 0);
+}
+
 constexpr uint32_t EXEC_WARPS = 4;
 constexpr uint32_t EXEC_MAX_RUN = 127;                      // longest literal run / match the fast path takes
 constexpr uint32_t EXEC_MASK_WORDS = (32 * 2 * EXEC_MAX_RUN + 31) / 32 + 4;
@@ -880,7 +916,9 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
         if (hs && hpos == 1) bs = hs;
         else if (aux[b].status) bs = aux[b].status;
         else if (hs) bs = hs;
-        else if (aux[b].pad) bs = aux[b].pad;
+        // the sequence-stage status (aux.pad) is only known when k_fse has finished the block: checked after the
+        // sequences have been consumed; it takes precedence over an execution error, as in the reference where
+        // decode_sequences completes before execute_sequences starts (block_decoder.rs:176-183)
         if (bs) { status = bs; err_block = d.block_in_frame; break; }
 
         if (d.btype == BT_RAW) {
@@ -902,14 +940,31 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
             const bool resolved = d.fse_resolves != 0;
             const uint32_t *seqs = seq_scratch + d.seq_buf_off * 3;
             __syncwarp();
-            // sequence records are prefetched one batch ahead (they stream from HBM exactly once)
+            // sequence records stream in from k_fse, which may still be decoding this block: `avail` = published count.
+            // Records are prefetched one batch ahead when they are already there.
+            uint32_t avail = 0;
             uint32_t nx_ll = 0, nx_ml = 0, nx_of = 1;
-            if (lane < d.nseq) { const uint32_t *s = seqs + (uint64_t)lane * 3; nx_ll = __ldg(s); nx_ml = __ldg(s + 1); nx_of = __ldg(s + 2); }
+            bool nx_loaded = false;
             for (uint32_t base = 0; base < d.nseq && !e; base += 32) {
                 const uint32_t nb = d.nseq - base < 32 ? d.nseq - base : 32;
-                const uint32_t my_ll = nx_ll, my_ml = nx_ml, my_of = nx_of;
-                nx_ll = 0; nx_ml = 0; nx_of = 1;
-                if (base + 32 + lane < d.nseq) { const uint32_t *s = seqs + (uint64_t)(base + 32 + lane) * 3; nx_ll = __ldg(s); nx_ml = __ldg(s + 1); nx_of = __ldg(s + 2); }
+                if (avail < base + nb) {
+                    avail = exec_wait_progress(aux, b, base + nb, lane);
+                    if (avail == 0xFFFFFFFEu) { e = B200Z_ERR_CUDA; break; }
+                }
+                uint32_t my_ll = nx_ll, my_ml = nx_ml, my_of = nx_of;
+                if (!nx_loaded) {
+                    my_ll = 0; my_ml = 0; my_of = 1;
+                    if (lane < nb) { const uint32_t *s = seqs + (uint64_t)(base + lane) * 3; my_ll = ld_cg_u32(s); my_ml = ld_cg_u32(s + 1); my_of = ld_cg_u32(s + 2); }
+                }
+                nx_ll = 0; nx_ml = 0; nx_of = 1; nx_loaded = false;
+                if (base + 32 < d.nseq) {
+                    const uint32_t nb2 = d.nseq - base - 32 < 32 ? d.nseq - base - 32 : 32;
+                    if (avail < base + 32 + nb2) avail = ld_acquire_u32(&aux[b].progress);   // one look, no waiting
+                    if (avail >= base + 32 + nb2) {
+                        nx_loaded = true;
+                        if (lane < nb2) { const uint32_t *s = seqs + (uint64_t)(base + 32 + lane) * 3; nx_ll = ld_cg_u32(s); nx_ml = ld_cg_u32(s + 1); nx_of = ld_cg_u32(s + 2); }
+                    }
+                }
                 // inclusive scans of ll and ll + ml
                 uint32_t lit_end = my_ll, out_end = my_ll + my_ml;
 #pragma unroll
@@ -1022,8 +1077,15 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
                     st.produced += rest; st.counter += rest;
                 }
             }
+            if (d.nseq && !hs) {
+                // the block's sequence stage must be over before its verdict (and the history it resolved) can be read
+                uint32_t fin = exec_wait_progress(aux, b, FSE_PROGRESS_FINAL, lane);
+                uint32_t st_seq = ld_cg_u32(&aux[b].pad);
+                if (fin == 0xFFFFFFFEu) st_seq = mk_status(B200Z_ERR_CUDA, B200Z_STAGE_SEQUENCES);
+                if (st_seq) { status = st_seq; err_block = d.block_in_frame; break; }
+            }
             if (e) { status = mk_status(e, e == B200Z_ERR_TARGET_TOO_SMALL ? B200Z_STAGE_DRAIN : B200Z_STAGE_EXECUTE); err_block = d.block_in_frame; break; }
-            if (resolved && d.nseq) { st.h0 = aux[b].hist_after[0]; st.h1 = aux[b].hist_after[1]; st.h2 = aux[b].hist_after[2]; }
+            if (resolved && d.nseq) { st.h0 = ld_cg_u32(&aux[b].hist_after[0]); st.h1 = ld_cg_u32(&aux[b].hist_after[1]); st.h2 = ld_cg_u32(&aux[b].hist_after[2]); }
         }
         __syncwarp();
         blocks_done++;
@@ -1089,17 +1151,17 @@ int launch_pipeline(const PipelineArgs &a, cudaStream_t s) {
 // idle (a few latency-bound warps per SM): run them side by side -- k_huf on the side stream, forked after
 // k_setup and joined before k_exec.
 int launch_pipeline_overlapped(const PipelineArgs &a, const PipelineStreams &ps) {
+    // main: k_setup -> k_fse.   side (forked after k_setup): k_huf -> k_exec, which consumes sequences while k_fse is
+    // still producing them (per-block progress counters).  k_fse is submitted before anything that could wait on it.
     int e;
     if ((e = launch_stage(a, 0, ps.main))) return e;
-    if (a.nblocks) {
-        if ((e = (int)cudaEventRecord(ps.fork, ps.main))) return e;
-        if ((e = (int)cudaStreamWaitEvent(ps.side, ps.fork, 0))) return e;
-        if ((e = launch_stage(a, 1, ps.side))) return e;
-        if ((e = (int)cudaEventRecord(ps.join, ps.side))) return e;
-        if ((e = launch_stage(a, 2, ps.main))) return e;
-        if ((e = (int)cudaStreamWaitEvent(ps.main, ps.join, 0))) return e;
-    }
-    return launch_stage(a, 3, ps.main);
+    if ((e = (int)cudaEventRecord(ps.fork, ps.main))) return e;
+    if ((e = launch_stage(a, 2, ps.main))) return e;
+    if ((e = (int)cudaStreamWaitEvent(ps.side, ps.fork, 0))) return e;
+    if ((e = launch_stage(a, 1, ps.side))) return e;
+    if ((e = launch_stage(a, 3, ps.side))) return e;
+    if ((e = (int)cudaEventRecord(ps.join, ps.side))) return e;
+    return (int)cudaStreamWaitEvent(ps.main, ps.join, 0);
 }
 
 uint32_t pipeline_launch_count(const PipelineArgs &a) { return (a.nblocks ? 3u : 0u) + (a.nframes ? 1u : 0u); }
