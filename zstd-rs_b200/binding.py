@@ -87,6 +87,7 @@ def lib():
         "b200z_batch_run": (C.c_int, [vp, vp, sz]),
         "b200z_batch_finish": (C.c_int, [vp, vp]),
         "b200z_batch_run_profile": (C.c_int, [vp, vp, sz, C.POINTER(C.c_float), sz]),
+        "b200z_batch_run_timeline": (C.c_int, [vp, vp, sz, C.POINTER(C.c_float), sz]),
         "b200z_num_stages": (C.c_int, []),
         "b200z_stage_kernel_name": (C.c_char_p, [C.c_int]),
         "b200z_batch_info": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
@@ -307,6 +308,13 @@ class Batch:
         ms = (C.c_float * n)()
         self.ctx._chk(self.ctx.L.b200z_batch_run_profile(self.h, op, ol, ms, n))
         return {self.ctx.L.b200z_stage_kernel_name(i).decode(): float(ms[i]) for i in range(n)}
+
+    def run_timeline(self, d_output):
+        """Completion time (ms from the start of the pass) of each kernel in the overlapped launch."""
+        op, ol, _k = _ptr(d_output)
+        ms = (C.c_float * 4)()
+        self.ctx._chk(self.ctx.L.b200z_batch_run_timeline(self.h, op, ol, ms, 4))
+        return {"k_setup": float(ms[0]), "k_huf": float(ms[1]), "k_fse": float(ms[2]), "k_exec": float(ms[3])}
 
     def finish(self):
         res = np.zeros(len(self.frames), dtype=FRAME_RESULT_DTYPE)

@@ -501,6 +501,40 @@ extern "C" int b200z_batch_run_profile(b200z_batch *b, uint8_t *d_output, size_t
     b->ran = true;
     return 0;
 }
+// One overlapped pass (as b200z_batch_run launches it) with an event after every kernel on its own stream:
+// out_ms[0..3] = completion time of k_setup, k_huf, k_fse, k_exec relative to the start of the pass.
+extern "C" int b200z_batch_run_timeline(b200z_batch *b, uint8_t *d_output, size_t output_cap, float *out_ms, size_t n) {
+    if (!b || !out_ms || n < 4) return B200Z_ERR_INVALID_ARGUMENT;
+    b200z_ctx *c = b->ctx;
+    if (int e = c->use()) return e;
+    Submission &s = b->sub;
+    if (!s.states.empty())
+        CU(c, cudaMemcpyAsync(s.d_states.p, b->d_states_init.p, s.states.size() * sizeof(FrameState), cudaMemcpyDeviceToDevice, c->stream));
+    PipelineArgs a = s.args(b->d_input, d_output, output_cap);
+    cudaEvent_t ev[5];
+    for (auto &e : ev) CU(c, cudaEventCreate(&e));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaEventRecord(ev[0], c->stream));
+    int le = launch_stage(a, 0, c->stream);
+    CU(c, cudaEventRecord(ev[1], c->stream));
+    if (!le) le = launch_stage(a, 1, c->stream);
+    CU(c, cudaEventRecord(ev[2], c->stream));
+    CU(c, cudaEventRecord(c->ev_fork, c->stream));
+    if (!le) le = launch_stage(a, 2, c->stream);
+    CU(c, cudaEventRecord(ev[3], c->stream));
+    CU(c, cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    if (!le) le = launch_stage(a, 3, c->side);
+    CU(c, cudaEventRecord(ev[4], c->side));
+    CU(c, cudaEventRecord(c->ev_join, c->side));
+    CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    if (le) return c->set_cuda_err((cudaError_t)le, "launch_stage");
+    c->launches += pipeline_launch_count(a);
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaStreamSynchronize(c->side));
+    for (int i = 0; i < 4; i++) CU(c, cudaEventElapsedTime(&out_ms[i], ev[0], ev[i + 1]));
+    for (auto &e : ev) cudaEventDestroy(e);
+    return 0;
+}
 extern "C" int b200z_num_stages(void) { return kNumStages; }
 extern "C" const char *b200z_stage_kernel_name(int stage) { return stage >= 0 && stage < kNumStages ? kStageNames[stage] : ""; }
 

@@ -891,10 +891,12 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
                                                         const uint32_t *__restrict__ seq_scratch, uint8_t *__restrict__ output, uint64_t output_cap,
                                                         uint32_t nframes) {
     __shared__ uint32_t s_mask[EXEC_WARPS][EXEC_MASK_WORDS];
+    __shared__ uint4 s_recs[EXEC_WARPS][32];
     const uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31, lt = lanemask_lt(), le = lt | (1u << lane);
+    const uint32_t lane = threadIdx.x & 31, lt = lanemask_lt();
     if (f >= nframes) return;
     uint32_t *mask = s_mask[threadIdx.x >> 5];
+    uint4 *recs = s_recs[threadIdx.x >> 5];
     const FrameDesc &fd = frames[f];
     FrameState fs = states[f];
     ExecState st;
@@ -1001,16 +1003,21 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
                     continue;
                 }
                 // ---------------- fast path
-                const uint32_t m_start = out_end - my_ml;            // batch-relative start of my match
-                const uint32_t pack = m_start | (out_end << 16);       // T <= 8128 < 2^16
+                // Sequence j owns the bytes [lit_begin_j, out_end_j): its literal run, then its match.  A bit is set at
+                // the last byte of every sequence, so the owner of output byte q is the number of set bits below q;
+                // one 16-byte shared-memory record per sequence then tells the byte where it comes from.
+                const uint32_t m_start = out_end - my_ml;              // batch-relative start of my match
+                const uint32_t lit_begin = m_start - my_ll;
                 const uint32_t l_start = st.litpos + lit_end - my_ll;  // literal index of my literal run
                 const uint32_t nrows = (T + 31) >> 5;
                 for (uint32_t w = lane; w < ((nrows + 3u) & ~3u); w += 32) mask[w] = 0;
+                recs[lane] = make_uint4(lit_begin | (m_start << 16), my_off, l_start, 0);
                 __syncwarp();
-                if (lane < nb) atomicOr(&mask[m_start >> 5], 1u << (m_start & 31u));
+                if (lane < nb) atomicOr(&mask[(out_end - 1) >> 5], 1u << ((out_end - 1) & 31u));
                 __syncwarp();
                 uint8_t *bout = out + st.produced;
-                uint32_t before = 0;   // match starts in earlier rows
+                const uint8_t *litp = lit.p;
+                uint32_t before = 0;   // sequences ended in earlier rows
                 // rows are produced four at a time: every byte whose source lies before the chunk (literals, and
                 // matches reaching back past the chunk start) is loaded first -- up to 4 independent loads per lane
                 // in flight -- then stored; the few bytes whose source lies inside the chunk follow, row by row.
@@ -1019,30 +1026,24 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
                     uint32_t val[4]; int32_t spv[4]; uint32_t kind[4];   // kind: 0 none, 1 stored in phase 1, 2 dependent match
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        const uint32_t r = r0 + i;
-                        const uint32_t q = (r << 5) + lane;
-                        const uint32_t word = r < nrows ? mask[r] : 0u;
-                        const uint32_t jm = before + __popc(word & le);   // match starts at or before q
+                        const uint32_t q = ((r0 + i) << 5) + lane;
+                        const uint32_t word = mask[r0 + i];
+                        const uint32_t owner = before + __popc(word & lt);   // sequences that ended below q
                         before += __popc(word);
-                        const uint32_t c = jm ? jm - 1 : 0;
-                        const uint32_t pk = __shfl_sync(0xffffffffu, pack, c);
-                        const uint32_t off = __shfl_sync(0xffffffffu, my_off, c);
-                        const uint32_t ls = __shfl_sync(0xffffffffu, l_start, jm & 31u);
-                        const bool valid = q < T;
-                        const uint32_t mend = pk >> 16, mst = pk & 0xffffu;
-                        const bool is_match = valid && jm && q < mend;
+                        const uint4 rc = recs[owner & 31u];
+                        const uint32_t mst = rc.x >> 16;
                         kind[i] = 0; val[i] = 0; spv[i] = 0;
-                        if (valid && !is_match) {
-                            // literal run of sequence jm starts where match jm-1 ended (or at the batch start)
-                            const uint32_t li = ls + (q - (jm ? mend : 0u));
-                            val[i] = lit.rle ? lit.byte : lit.p[li];
-                            kind[i] = 1;
-                        } else if (is_match) {
-                            uint32_t kk = q - mst;
-                            if (kk >= off) kk %= off;
-                            const int32_t sp = (int32_t)mst - (int32_t)off + (int32_t)kk;   // batch-relative source
-                            spv[i] = sp;
-                            if (sp < chunk0) { val[i] = bout[sp]; kind[i] = 1; } else kind[i] = 2;
+                        if (q < T) {
+                            if (q < mst) {
+                                val[i] = litp[rc.z + (q - (rc.x & 0xffffu))];
+                                kind[i] = 1;
+                            } else {
+                                uint32_t kk = q - mst;
+                                if (kk >= rc.y) kk %= rc.y;                  // overlapping match: byte k comes from k mod offset
+                                const int32_t sp = (int32_t)mst - (int32_t)rc.y + (int32_t)kk;   // batch-relative source
+                                spv[i] = sp;
+                                if (sp < chunk0) { val[i] = bout[sp]; kind[i] = 1; } else kind[i] = 2;
+                            }
                         }
                     }
 #pragma unroll
@@ -1115,6 +1116,11 @@ int init_kernels() {
     cudaError_t e = cudaFuncSetAttribute(k_fse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFseSmem);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_huf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHufSmem);
+    if (e != cudaSuccess) return (int)e;
+    // k_fse and k_exec share SMs: ask for the largest shared-memory carve-out so that both fit
+    e = cudaFuncSetAttribute(k_fse, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_exec, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     return (int)e;
 }
 
@@ -1151,14 +1157,16 @@ int launch_pipeline(const PipelineArgs &a, cudaStream_t s) {
 // idle (a few latency-bound warps per SM): run them side by side -- k_huf on the side stream, forked after
 // k_setup and joined before k_exec.
 int launch_pipeline_overlapped(const PipelineArgs &a, const PipelineStreams &ps) {
-    // main: k_setup -> k_fse.   side (forked after k_setup): k_huf -> k_exec, which consumes sequences while k_fse is
-    // still producing them (per-block progress counters).  k_fse is submitted before anything that could wait on it.
+    // main: k_setup -> k_huf -> k_fse.   side (forked after k_huf): k_exec, which consumes sequences while k_fse is still
+    // producing them (per-block progress counters).  k_fse is submitted first and on the high-priority stream, so its
+    // CTAs are always placed before k_exec's.  (k_huf cannot share an SM with k_fse: 2 x 86 KiB + 29 KiB of shared
+    // memory do not fit the carve-out, so it runs before it.)
     int e;
     if ((e = launch_stage(a, 0, ps.main))) return e;
+    if ((e = launch_stage(a, 1, ps.main))) return e;
     if ((e = (int)cudaEventRecord(ps.fork, ps.main))) return e;
     if ((e = launch_stage(a, 2, ps.main))) return e;
     if ((e = (int)cudaStreamWaitEvent(ps.side, ps.fork, 0))) return e;
-    if ((e = launch_stage(a, 1, ps.side))) return e;
     if ((e = launch_stage(a, 3, ps.side))) return e;
     if ((e = (int)cudaEventRecord(ps.join, ps.side))) return e;
     return (int)cudaStreamWaitEvent(ps.main, ps.join, 0);
