@@ -13,6 +13,7 @@
 //
 // Integer/byte work only; the roofline is HBM bandwidth.
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 
 #include "kernels.h"
@@ -1017,13 +1018,17 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
                 __syncwarp();
                 uint8_t *bout = out + st.produced;
                 const uint8_t *litp = lit.p;
+                asm volatile("" : "+l"(bout), "+l"(litp));   // keep both bases as single 64-bit registers (one add per access)
                 uint32_t before = 0;   // sequences ended in earlier rows
                 // rows are produced four at a time: every byte whose source lies before the chunk (literals, and
                 // matches reaching back past the chunk start) is loaded first -- up to 4 independent loads per lane
                 // in flight -- then stored; the few bytes whose source lies inside the chunk follow, row by row.
                 for (uint32_t r0 = 0; r0 < nrows; r0 += 4) {
                     const int32_t chunk0 = (int32_t)(r0 << 5);
-                    uint32_t val[4]; int32_t spv[4]; uint32_t kind[4];   // kind: 0 none, 1 stored in phase 1, 2 dependent match
+                    // tag: TAG_NONE = nothing to do, TAG_STORE = value loaded in phase 1, otherwise the (batch-relative,
+                    // >= chunk0) source position of a match byte that depends on this chunk
+                    constexpr int32_t TAG_NONE = INT32_MIN, TAG_STORE = INT32_MIN + 1;
+                    uint32_t val[4]; int32_t tag[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         const uint32_t q = ((r0 + i) << 5) + lane;
@@ -1032,35 +1037,34 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
                         before += __popc(word);
                         const uint4 rc = recs[owner & 31u];
                         const uint32_t mst = rc.x >> 16;
-                        kind[i] = 0; val[i] = 0; spv[i] = 0;
+                        tag[i] = TAG_NONE; val[i] = 0;
                         if (q < T) {
                             if (q < mst) {
                                 val[i] = litp[rc.z + (q - (rc.x & 0xffffu))];
-                                kind[i] = 1;
+                                tag[i] = TAG_STORE;
                             } else {
                                 uint32_t kk = q - mst;
                                 if (kk >= rc.y) kk %= rc.y;                  // overlapping match: byte k comes from k mod offset
                                 const int32_t sp = (int32_t)mst - (int32_t)rc.y + (int32_t)kk;   // batch-relative source
-                                spv[i] = sp;
-                                if (sp < chunk0) { val[i] = bout[sp]; kind[i] = 1; } else kind[i] = 2;
+                                tag[i] = sp;
+                                if (sp < chunk0) { val[i] = bout[sp]; tag[i] = TAG_STORE; }
                             }
                         }
                     }
 #pragma unroll
                     for (int i = 0; i < 4; i++)
-                        if (kind[i] == 1) bout[((r0 + i) << 5) + lane] = (uint8_t)val[i];
+                        if (tag[i] == TAG_STORE) bout[((r0 + i) << 5) + lane] = (uint8_t)val[i];
                     // dependent bytes (source inside this chunk), rows in order
-                    uint32_t anydep = __ballot_sync(0xffffffffu, kind[0] == 2 || kind[1] == 2 || kind[2] == 2 || kind[3] == 2);
-                    if (anydep) {
+                    if (__any_sync(0xffffffffu, (tag[0] >= chunk0) | (tag[1] >= chunk0) | (tag[2] >= chunk0) | (tag[3] >= chunk0))) {
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
-                            uint32_t pending = __ballot_sync(0xffffffffu, kind[i] == 2);
+                            bool mine = tag[i] >= chunk0;
+                            uint32_t pending = __ballot_sync(0xffffffffu, mine);
                             const int32_t row0 = chunk0 + (i << 5);
-                            bool mine = kind[i] == 2;
                             while (pending) {
                                 __syncwarp();
-                                bool ready = mine && (spv[i] < row0 || !((pending >> (spv[i] - row0)) & 1u));
-                                if (ready) { bout[row0 + (int32_t)lane] = bout[spv[i]]; mine = false; }
+                                bool ready = mine && (tag[i] < row0 || !((pending >> (tag[i] - row0)) & 1u));
+                                if (ready) { bout[row0 + (int32_t)lane] = bout[tag[i]]; mine = false; }
                                 pending &= ~__ballot_sync(0xffffffffu, ready);
                             }
                         }
