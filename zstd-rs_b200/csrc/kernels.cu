@@ -1018,7 +1018,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
                 __syncwarp();
                 uint8_t *bout = out + st.produced;
                 const uint8_t *litp = lit.p;
-                const long long lit_delta = (long long)(litp - bout);   // literals addressed relative to the output base: one load path
+                asm volatile("" : "+l"(bout), "+l"(litp));   // keep both bases as single 64-bit registers (one add per access)
                 uint32_t before = 0;   // sequences ended in earlier rows
                 // rows are produced four at a time: every byte whose source lies before the chunk (literals, and
                 // matches reaching back past the chunk start) is loaded first -- up to 4 independent loads per lane
@@ -1037,17 +1037,19 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
                         before += __popc(word);
                         const uint4 rc = recs[owner & 31u];
                         const uint32_t mst = rc.x >> 16;
-                        const bool valid = q < T, is_lit = q < mst;
-                        uint32_t kk = q - mst;
-                        if (valid && !is_lit && kk >= rc.y) kk %= rc.y;      // overlapping match: byte k comes from k mod offset (rare)
-                        const int32_t sp = (int32_t)mst - (int32_t)rc.y + (int32_t)kk;   // batch-relative source of a match byte
-                        const uint32_t li = rc.z + q - (rc.x & 0xffffu);                  // literal index of a literal byte
-                        const bool dep = valid && !is_lit && sp >= chunk0;
-                        // one load for both kinds: literals live at bout + lit_delta
-                        const long long offs = is_lit ? (long long)li + lit_delta : (long long)sp;
-                        val[i] = 0;
-                        if (valid && !dep) val[i] = bout[offs];
-                        tag[i] = dep ? sp : ((valid && !dep) ? TAG_STORE : TAG_NONE);
+                        tag[i] = TAG_NONE; val[i] = 0;
+                        if (q < T) {
+                            if (q < mst) {
+                                val[i] = litp[rc.z + (q - (rc.x & 0xffffu))];
+                                tag[i] = TAG_STORE;
+                            } else {
+                                uint32_t kk = q - mst;
+                                if (kk >= rc.y) kk %= rc.y;                  // overlapping match: byte k comes from k mod offset
+                                const int32_t sp = (int32_t)mst - (int32_t)rc.y + (int32_t)kk;   // batch-relative source
+                                tag[i] = sp;
+                                if (sp < chunk0) { val[i] = bout[sp]; tag[i] = TAG_STORE; }
+                            }
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < 4; i++)
