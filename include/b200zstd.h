@@ -159,6 +159,13 @@ void b200z_ctx_destroy(b200z_ctx *ctx);
 const char *b200z_ctx_last_error_message(const b200z_ctx *ctx);
 /* the CUDA stream (cudaStream_t as void*) all work of this ctx is enqueued on; for event timing by callers */
 void *b200z_ctx_stream(const b200z_ctx *ctx);
+/* Context flags.  B200Z_FLAG_CHECKSUM: the batch entry also computes every frame's content checksum on the GPU (XXH64 seed 0 over
+ * the plaintext, the hash the reference feeds while draining, decode_buffer.rs:225-226,290,301) and returns it in
+ * b200z_frame_result.calculated_checksum -- like the reference it is reported, never enforced (frame_decoder.rs:253-270).
+ * Device output buffers must be readable 8 bytes past their end when this flag is set. */
+#define B200Z_FLAG_CHECKSUM 1u
+void b200z_ctx_set_flags(b200z_ctx *ctx, uint32_t flags);
+uint32_t b200z_ctx_flags(const b200z_ctx *ctx);
 /* number of this library's kernel launches since ctx creation (bench.py's gpu_launches) */
 uint64_t b200z_ctx_kernel_launches(const b200z_ctx *ctx);
 
@@ -203,6 +210,8 @@ typedef struct b200z_frame_result {
     uint32_t checksum_from_data;  /* get_checksum_from_data (frame_decoder.rs:254)                         */
     uint32_t has_dict_id;
     uint32_t dict_id;        /* FrameHeader::dictionary_id (frame.rs:142)                                  */
+    uint32_t has_calculated_checksum; /* 1 when the context ran the GPU checksum stage (B200Z_FLAG_CHECKSUM)   */
+    uint32_t calculated_checksum;     /* get_calculated_checksum (frame_decoder.rs:262): XXH64(seed 0) low 32 bits */
 } b200z_frame_result;
 
 #define B200Z_MEM_HOST 0

@@ -77,6 +77,35 @@ def test_corpus_batch_and_intermediates(pkg, ctx, oracle, manifest):
     assert nlit > 1000 and nseq > 1_000_000   # 2458 compressed blocks / 1,031,936 sequences in the corpus
 
 
+def test_gpu_checksum_stage(pkg, manifest):
+    """B200Z_FLAG_CHECKSUM: XXH64 on the GPU == the stored content checksum for all 101 corpus frames (tests/decode_corpus.rs:61-74),
+    incl. empty and tiny frames, and == the host hash for random lengths around the 32-byte stripe boundary."""
+    import torch
+    c2 = pkg.Context(0)
+    c2.set_flags(pkg.binding.FLAG_CHECKSUM)
+    names = sorted(manifest["corpus"])
+    frames = [read_golden("decodecorpus", n) for n in names]
+    sizes = [manifest["corpus"][n]["size"] for n in names]
+    io, comp, total = _io(pkg, frames, sizes)
+    d_out = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
+    b = pkg.Batch(c2, comp, io)
+    b.run(d_out)
+    res = b.finish()
+    for i, n in enumerate(names):
+        assert res[i]["status"] == 0 and res[i]["has_calculated_checksum"] == 1, n
+        assert res[i]["calculated_checksum"] == res[i]["checksum_from_data"] == manifest["corpus"][n]["xxh64_low32"], n
+    import datagen as G
+    rng = np.random.Generator(np.random.PCG64(9))
+    pieces = [rng.integers(0, 256, int(n), dtype=np.uint8) for n in list(range(0, 70)) + [255, 256, 257, 4095, 4096, 4097, 65537]]
+    frames = [G.compress(p_, level=1) for p_ in pieces]
+    io, comp, total = _io(pkg, frames, [len(p_) for p_ in pieces])
+    out = np.zeros(total + 64, dtype=np.uint8)
+    res = pkg.decode_frames(c2, comp, io, out)
+    for i, p_ in enumerate(pieces):
+        assert res[i]["status"] == 0 and res[i]["calculated_checksum"] == (pkg.xxh64(p_.tobytes()) & 0xFFFFFFFF) == res[i]["checksum_from_data"], len(p_)
+    c2.close()
+
+
 def test_dict_corpus(pkg, ctx, manifest):
     """tests/dict_test.rs:77-262 via the mirror, then all 207 frames in one batch."""
     dic = read_golden("dict_tests", "dictionary")

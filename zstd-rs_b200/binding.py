@@ -24,6 +24,7 @@ WRITE_FN = C.CFUNCTYPE(C.c_long, C.c_void_p, C.POINTER(C.c_uint8), C.c_size_t)
 ALL, UPTO_BLOCKS, UPTO_BYTES = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 ERR_SKIP_FRAME = 8
+FLAG_CHECKSUM = 1
 
 
 class FrameIO(C.Structure):
@@ -33,13 +34,15 @@ class FrameIO(C.Structure):
 class FrameResult(C.Structure):
     _fields_ = [("out_size", C.c_uint64), ("bytes_read", C.c_uint64), ("content_size", C.c_uint64), ("window_size", C.c_uint64),
                 ("status", C.c_int32), ("stage", C.c_int32), ("blocks_decoded", C.c_uint32), ("error_block", C.c_uint32),
-                ("has_checksum", C.c_uint32), ("checksum_from_data", C.c_uint32), ("has_dict_id", C.c_uint32), ("dict_id", C.c_uint32)]
+                ("has_checksum", C.c_uint32), ("checksum_from_data", C.c_uint32), ("has_dict_id", C.c_uint32), ("dict_id", C.c_uint32),
+                ("has_calculated_checksum", C.c_uint32), ("calculated_checksum", C.c_uint32)]
 
 
 FRAME_IO_DTYPE = np.dtype([("src_off", "<u8"), ("src_size", "<u8"), ("out_off", "<u8"), ("out_cap", "<u8")])
 FRAME_RESULT_DTYPE = np.dtype([("out_size", "<u8"), ("bytes_read", "<u8"), ("content_size", "<u8"), ("window_size", "<u8"),
                                ("status", "<i4"), ("stage", "<i4"), ("blocks_decoded", "<u4"), ("error_block", "<u4"),
-                               ("has_checksum", "<u4"), ("checksum_from_data", "<u4"), ("has_dict_id", "<u4"), ("dict_id", "<u4")])
+                               ("has_checksum", "<u4"), ("checksum_from_data", "<u4"), ("has_dict_id", "<u4"), ("dict_id", "<u4"),
+                               ("has_calculated_checksum", "<u4"), ("calculated_checksum", "<u4")])
 assert FRAME_IO_DTYPE.itemsize == C.sizeof(FrameIO) and FRAME_RESULT_DTYPE.itemsize == C.sizeof(FrameResult)
 
 
@@ -76,6 +79,8 @@ def lib():
         "b200z_ctx_last_error_message": (C.c_char_p, [vp]),
         "b200z_ctx_stream": (vp, [vp]),
         "b200z_ctx_kernel_launches": (C.c_uint64, [vp]),
+        "b200z_ctx_set_flags": (None, [vp, C.c_uint32]),
+        "b200z_ctx_flags": (C.c_uint32, [vp]),
         "b200z_dict_create": (C.c_int, [vp, vp, sz, pp]),
         "b200z_dict_create_raw_content": (C.c_int, [vp, C.c_uint32, vp, sz, pp]),
         "b200z_dict_id": (C.c_uint32, [vp]),
@@ -207,6 +212,10 @@ class Context:
 
     def kernel_launches(self):
         return self.L.b200z_ctx_kernel_launches(self.h)
+
+    def set_flags(self, flags):
+        """FLAG_CHECKSUM = 1: the batch entry also computes each frame's XXH64 content checksum on the GPU."""
+        self.L.b200z_ctx_set_flags(self.h, flags)
 
     def _chk(self, e):
         if e:

@@ -85,6 +85,7 @@ struct b200z_ctx {
     FseSlot *d_predef = nullptr;
     std::string err;
     uint64_t launches = 0;
+    uint32_t flags = 0;
     int set_cuda_err(cudaError_t e, const char *what) {
         char buf[256];
         snprintf(buf, sizeof buf, "CUDA error in %s: %s", what, cudaGetErrorString(e));
@@ -139,6 +140,8 @@ extern "C" void b200z_ctx_destroy(b200z_ctx *c) {
 extern "C" const char *b200z_ctx_last_error_message(const b200z_ctx *c) { return c ? c->err.c_str() : ""; }
 extern "C" void *b200z_ctx_stream(const b200z_ctx *c) { return c ? (void *)c->stream : nullptr; }
 extern "C" uint64_t b200z_ctx_kernel_launches(const b200z_ctx *c) { return c ? c->launches : 0; }
+extern "C" void b200z_ctx_set_flags(b200z_ctx *c, uint32_t flags) { if (c) c->flags = flags; }
+extern "C" uint32_t b200z_ctx_flags(const b200z_ctx *c) { return c ? c->flags : 0; }
 extern "C" uint64_t b200z_xxh64(const uint8_t *data, size_t len) { XXH64State s; s.reset(); s.update(data, len); return s.digest(); }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -339,6 +342,7 @@ struct b200z_batch {
     DevBuf d_states_init;
     size_t input_len = 0;
     bool ran = false;
+    bool checksummed = false;
 };
 
 static int plan_batch(b200z_batch *b, const uint8_t *in, size_t in_len, const b200z_frame_io *frames, size_t nframes,
@@ -473,6 +477,12 @@ extern "C" int b200z_batch_run(b200z_batch *b, uint8_t *d_output, size_t output_
     int e = launch_pipeline_overlapped(a, ps);
     if (e) return c->set_cuda_err((cudaError_t)e, "launch_pipeline");
     c->launches += pipeline_launch_count(a);
+    b->checksummed = false;
+    if ((c->flags & B200Z_FLAG_CHECKSUM) && a.nframes) {
+        if ((e = launch_checksum(a, c->stream))) return c->set_cuda_err((cudaError_t)e, "launch_checksum");
+        c->launches += 1;
+        b->checksummed = true;
+    }
     b->ran = true;
     return 0;
 }
@@ -551,6 +561,7 @@ static void fill_result(const b200z_batch *b, size_t i, const FrameState *st, b2
     r.out_size = st->produced; r.blocks_decoded = st->blocks_done;
     if (st->status == 0) {
         r.bytes_read = fi.bytes_read_full; r.has_checksum = fi.has_checksum; r.checksum_from_data = fi.checksum;
+        if (b->checksummed) { r.has_calculated_checksum = 1; r.calculated_checksum = (uint32_t)st->xxh64; }
         return;
     }
     r.status = (int32_t)(st->status & 0xffffu); r.stage = (int32_t)((st->status >> 16) & 0xffu); r.error_block = st->error_block;
@@ -724,6 +735,12 @@ static int decode_frames_pipelined(b200z_ctx *c, const uint8_t *input, size_t in
         int le = launch_pipeline_overlapped(a, ps);
         if (le) return c->set_cuda_err((cudaError_t)le, "launch_pipeline");
         c->launches += pipeline_launch_count(a);
+        b->checksummed = false;
+        if ((c->flags & B200Z_FLAG_CHECKSUM) && a.nframes) {
+            if ((le = launch_checksum(a, c->stream))) return c->set_cuda_err((cudaError_t)le, "launch_checksum");
+            c->launches += 1;
+            b->checksummed = true;
+        }
         CU(c, cudaEventRecord(p->ev_k[s], c->stream));
         CU(c, cudaStreamWaitEvent(p->s_d2h, p->ev_k[s], 0));
         size_t nst = b->sub.states.size();

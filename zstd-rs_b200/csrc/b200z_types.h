@@ -118,6 +118,8 @@ struct alignas(16) FrameState {
     uint64_t counter;         // total_output_counter (quirk: Raw/RLE blocks and fully-in-dict matches not counted)
     uint32_t error_block;     // block_in_frame of the failing block
     uint32_t blocks_done;     // blocks fully executed
+    uint64_t xxh64;           // XXH64(seed 0) of the plaintext, when the checksum stage ran
+    uint64_t pad;
 };
 
 struct alignas(16) FrameDesc {

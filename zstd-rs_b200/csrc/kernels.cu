@@ -1104,6 +1104,56 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// k_xxh64: content checksum of every frame's plaintext, XXH64 seed 0 -- what DecodeBuffer feeds on drain
+// (decode_buffer.rs:42,225-226,290,301) and FrameDecoder::get_calculated_checksum truncates to 32 bits
+// (frame_decoder.rs:262-270).  The four accumulators of XXH64 are independent chains over every 4th 8-byte word:
+// four lanes per frame (8 frames per warp), each lane walks its own lane of the 32-byte stripes; lane 0 of the
+// group merges and finishes the tail.  Optional stage (B200Z_FLAG_CHECKSUM): it re-reads the output once.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ uint64_t ld_u64_unaligned(const uint8_t *p) {
+    uintptr_t a = (uintptr_t)p;
+    if ((a & 7) == 0) return *reinterpret_cast<const uint64_t *>(p);
+    const uint64_t *q = reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7);
+    uint32_t sh = (uint32_t)(a & 7) * 8u;
+    return (q[0] >> sh) | (q[1] << (64u - sh));
+}
+__global__ void k_xxh64(const FrameDesc *__restrict__ frames, FrameState *__restrict__ states, const uint8_t *__restrict__ output, uint32_t nframes) {
+    const uint64_t P1 = 0x9E3779B185EBCA87ull, P2 = 0xC2B2AE3D27D4EB4Full, P3 = 0x165667B19E3779F9ull, P4 = 0x85EBCA77C2B2AE63ull, P5 = 0x27D4EB2F165667C5ull;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t f = t >> 2, k = t & 3;
+    if (f >= nframes) return;
+    const FrameState &st = states[f];
+    const uint8_t *p = output + frames[f].out_off + st.drained;
+    const uint64_t len = st.status ? 0 : st.produced - st.drained;
+    const uint64_t nstripes = len >> 5;
+    uint64_t v = k == 0 ? P1 + P2 : (k == 1 ? P2 : (k == 2 ? 0ull : 0ull - P1));
+    const uint8_t *q = p + 8 * k;
+    for (uint64_t s = 0; s < nstripes; s++, q += 32) {
+        v += ld_u64_unaligned(q) * P2;
+        v = rotl64(v, 31) * P1;
+    }
+    const uint32_t gbase = (threadIdx.x & 31u) & ~3u;
+    uint64_t v0 = __shfl_sync(0xffffffffu, v, gbase), v1 = __shfl_sync(0xffffffffu, v, gbase + 1), v2 = __shfl_sync(0xffffffffu, v, gbase + 2),
+             v3 = __shfl_sync(0xffffffffu, v, gbase + 3);
+    if (k != 0) return;
+    uint64_t h;
+    if (len >= 32) {
+        h = rotl64(v0, 1) + rotl64(v1, 7) + rotl64(v2, 12) + rotl64(v3, 18);
+        uint64_t vs[4] = {v0, v1, v2, v3};
+#pragma unroll
+        for (int i = 0; i < 4; i++) { uint64_t x = rotl64(vs[i] * P2, 31) * P1; h ^= x; h = h * P1 + P4; }
+    } else h = P5;   // seed 0 + PRIME64_5
+    h += len;
+    const uint8_t *r = p + (nstripes << 5), *end = p + len;
+    while (r + 8 <= end) { uint64_t x = rotl64(ld_u64_unaligned(r) * P2, 31) * P1; h ^= x; h = rotl64(h, 27) * P1 + P4; r += 8; }
+    if (r + 4 <= end) { uint32_t w = (uint32_t)r[0] | ((uint32_t)r[1] << 8) | ((uint32_t)r[2] << 16) | ((uint32_t)r[3] << 24); h ^= (uint64_t)w * P1; h = rotl64(h, 23) * P2 + P3; r += 4; }
+    while (r < end) { h ^= (uint64_t)(*r) * P5; h = rotl64(h, 11) * P1; r++; }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    states[f].xxh64 = h;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------------
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
@@ -1149,6 +1199,11 @@ int launch_stage(const PipelineArgs &a, int stage, cudaStream_t s) {
             break;
         default: break;
     }
+    return (int)cudaGetLastError();
+}
+
+int launch_checksum(const PipelineArgs &a, cudaStream_t s) {
+    if (a.nframes) k_xxh64<<<cdiv(a.nframes * 4, 128), 128, 0, s>>>(a.frames, a.states, a.output, a.nframes);
     return (int)cudaGetLastError();
 }
 

@@ -27,6 +27,7 @@ constexpr int kNumStages = 4;
 extern const char *const kStageNames[kNumStages];
 int launch_stage(const PipelineArgs &a, int stage, cudaStream_t s);
 int launch_pipeline(const PipelineArgs &a, cudaStream_t s);
+int launch_checksum(const PipelineArgs &a, cudaStream_t s);   // optional 5th stage: XXH64 of every frame's plaintext
 struct PipelineStreams { cudaStream_t main, side; cudaEvent_t fork, join; };
 int launch_pipeline_overlapped(const PipelineArgs &a, const PipelineStreams &ps);
 uint32_t pipeline_launch_count(const PipelineArgs &a);
