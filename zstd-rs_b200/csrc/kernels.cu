@@ -884,7 +884,7 @@ __device__ __forceinline__ uint32_t exec_wait_progress(const BlockAux *aux, uint
 
 constexpr uint32_t EXEC_WARPS = 4;
 constexpr uint32_t EXEC_MAX_RUN = 127;                      // longest literal run / match the fast path takes
-constexpr uint32_t EXEC_MASK_WORDS = (32 * 2 * EXEC_MAX_RUN + 1 + 31) / 32 + 4;
+constexpr uint32_t EXEC_MASK_WORDS = (32 * 2 * EXEC_MAX_RUN + 31) / 32 + 4;
 
 __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__restrict__ descs, const BlockAux *__restrict__ aux,
                                                         const FrameDesc *__restrict__ frames, FrameState *__restrict__ states,
@@ -1007,91 +1007,65 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
                 // Sequence j owns the bytes [lit_begin_j, out_end_j): its literal run, then its match.  A bit is set at
                 // the last byte of every sequence, so the owner of output byte q is the number of set bits below q;
                 // one 16-byte shared-memory record per sequence then tells the byte where it comes from.
-                // Coordinates are relative to a 2-byte aligned origin (`sh` = 0 or 1 dummy bytes in front of the batch) so
-                // that every lane can own two adjacent bytes and store them with one aligned 16-bit store.
-                const uint32_t sh = (uint32_t)((uintptr_t)(out + st.produced) & 1u);
-                const uint32_t m_start = out_end - my_ml + sh;         // origin-relative start of my match
+                const uint32_t m_start = out_end - my_ml;              // batch-relative start of my match
                 const uint32_t lit_begin = m_start - my_ll;
                 const uint32_t l_start = st.litpos + lit_end - my_ll;  // literal index of my literal run
-                const uint32_t Ts = T + sh;
-                const uint32_t nwords = (Ts + 31) >> 5;
-                for (uint32_t w = lane; w < ((nwords + 3u) & ~3u); w += 32) mask[w] = 0;
+                const uint32_t nrows = (T + 31) >> 5;
+                for (uint32_t w = lane; w < ((nrows + 3u) & ~3u); w += 32) mask[w] = 0;
                 recs[lane] = make_uint4(lit_begin | (m_start << 16), my_off, l_start, 0);
                 __syncwarp();
-                if (lane < nb) atomicOr(&mask[(out_end + sh - 1) >> 5], 1u << ((out_end + sh - 1) & 31u));
+                if (lane < nb) atomicOr(&mask[(out_end - 1) >> 5], 1u << ((out_end - 1) & 31u));
                 __syncwarp();
-                uint8_t *bout = out + st.produced - sh;               // origin
+                uint8_t *bout = out + st.produced;
                 const uint8_t *litp = lit.p;
                 asm volatile("" : "+l"(bout), "+l"(litp));   // keep both bases as single 64-bit registers (one add per access)
-                uint32_t before = 0;   // sequences ended in earlier words
-                constexpr int32_t TAG_NONE = INT32_MIN, TAG_STORE = INT32_MIN + 1;
-                // 128 bytes (four mask words) per chunk = two rows of 64 bytes, two adjacent bytes per lane.  Every byte
-                // whose source lies before the chunk (literals, and matches reaching back past the chunk start) is loaded
-                // first -- four independent loads per lane in flight -- then stored; the few bytes whose source lies
-                // inside the chunk follow, row by row.
-                for (uint32_t w0 = 0; w0 < nwords; w0 += 4) {
-                    const int32_t chunk0 = (int32_t)(w0 << 5);
-                    uint32_t val[4]; int32_t tag[4];
-                    // tag: TAG_NONE = nothing to do, TAG_STORE = value loaded in phase 1, otherwise the (origin-relative,
+                uint32_t before = 0;   // sequences ended in earlier rows
+                // rows are produced four at a time: every byte whose source lies before the chunk (literals, and
+                // matches reaching back past the chunk start) is loaded first -- up to 4 independent loads per lane
+                // in flight -- then stored; the few bytes whose source lies inside the chunk follow, row by row.
+                for (uint32_t r0 = 0; r0 < nrows; r0 += 4) {
+                    const int32_t chunk0 = (int32_t)(r0 << 5);
+                    // tag: TAG_NONE = nothing to do, TAG_STORE = value loaded in phase 1, otherwise the (batch-relative,
                     // >= chunk0) source position of a match byte that depends on this chunk
-                    auto one_byte = [&](uint32_t q, const uint4 &rc, uint32_t &v, int32_t &tg) {
-                        tg = TAG_NONE; v = 0;
-                        if (q - sh < T) {
-                            const uint32_t mst = rc.x >> 16;
+                    constexpr int32_t TAG_NONE = INT32_MIN, TAG_STORE = INT32_MIN + 1;
+                    uint32_t val[4]; int32_t tag[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint32_t q = ((r0 + i) << 5) + lane;
+                        const uint32_t word = mask[r0 + i];
+                        const uint32_t owner = before + __popc(word & lt);   // sequences that ended below q
+                        before += __popc(word);
+                        const uint4 rc = recs[owner & 31u];
+                        const uint32_t mst = rc.x >> 16;
+                        tag[i] = TAG_NONE; val[i] = 0;
+                        if (q < T) {
                             if (q < mst) {
-                                v = litp[rc.z + (q - (rc.x & 0xffffu))];
-                                tg = TAG_STORE;
+                                val[i] = litp[rc.z + (q - (rc.x & 0xffffu))];
+                                tag[i] = TAG_STORE;
                             } else {
                                 uint32_t kk = q - mst;
                                 if (kk >= rc.y) kk %= rc.y;                  // overlapping match: byte k comes from k mod offset
-                                const int32_t sp = (int32_t)mst - (int32_t)rc.y + (int32_t)kk;   // origin-relative source
-                                tg = sp;
-                                if (sp < chunk0) { v = bout[sp]; tg = TAG_STORE; }
+                                const int32_t sp = (int32_t)mst - (int32_t)rc.y + (int32_t)kk;   // batch-relative source
+                                tag[i] = sp;
+                                if (sp < chunk0) { val[i] = bout[sp]; tag[i] = TAG_STORE; }
                             }
                         }
-                    };
-#pragma unroll
-                    for (int i = 0; i < 2; i++) {
-                        const uint32_t wlo = mask[w0 + 2 * i], whi = mask[w0 + 2 * i + 1];
-                        const uint32_t myw = lane < 16 ? wlo : whi;
-                        const uint32_t bit = (lane & 15u) << 1;
-                        const uint32_t owner0 = before + (lane < 16 ? 0u : __popc(wlo)) + __popc(myw & ((1u << bit) - 1u));
-                        const uint32_t e0 = (myw >> bit) & 1u;               // a sequence ends on my first byte
-                        before += __popc(wlo) + __popc(whi);
-                        const uint32_t q0 = ((w0 + 2 * i) << 5) + (lane << 1);
-                        const uint4 rc0 = recs[owner0 & 31u];
-                        uint4 rc1 = rc0;
-                        if (e0) rc1 = recs[(owner0 + 1) & 31u];
-                        one_byte(q0, rc0, val[2 * i], tag[2 * i]);
-                        one_byte(q0 + 1, rc1, val[2 * i + 1], tag[2 * i + 1]);
                     }
 #pragma unroll
-                    for (int i = 0; i < 2; i++) {
-                        uint8_t *dst = bout + ((w0 + 2 * i) << 5) + (lane << 1);
-                        if (tag[2 * i] == TAG_STORE && tag[2 * i + 1] == TAG_STORE) *reinterpret_cast<uint16_t *>(dst) = (uint16_t)(val[2 * i] | (val[2 * i + 1] << 8));
-                        else {
-                            if (tag[2 * i] == TAG_STORE) dst[0] = (uint8_t)val[2 * i];
-                            if (tag[2 * i + 1] == TAG_STORE) dst[1] = (uint8_t)val[2 * i + 1];
-                        }
-                    }
+                    for (int i = 0; i < 4; i++)
+                        if (tag[i] == TAG_STORE) bout[((r0 + i) << 5) + lane] = (uint8_t)val[i];
                     // dependent bytes (source inside this chunk), rows in order
                     if (__any_sync(0xffffffffu, (tag[0] >= chunk0) | (tag[1] >= chunk0) | (tag[2] >= chunk0) | (tag[3] >= chunk0))) {
 #pragma unroll
-                        for (int i = 0; i < 2; i++) {
-                            bool mine0 = tag[2 * i] >= chunk0, mine1 = tag[2 * i + 1] >= chunk0;
-                            uint32_t pm0 = __ballot_sync(0xffffffffu, mine0), pm1 = __ballot_sync(0xffffffffu, mine1);
-                            const int32_t row0 = chunk0 + (i << 6);
-                            uint8_t *dst = bout + row0 + (int32_t)(lane << 1);
-                            while (pm0 | pm1) {
+                        for (int i = 0; i < 4; i++) {
+                            bool mine = tag[i] >= chunk0;
+                            uint32_t pending = __ballot_sync(0xffffffffu, mine);
+                            const int32_t row0 = chunk0 + (i << 5);
+                            while (pending) {
                                 __syncwarp();
-                                // a source byte is final if it lies before this row or is not pending any more
-                                const int32_t p0 = tag[2 * i] - row0, p1 = tag[2 * i + 1] - row0;
-                                const bool r0 = mine0 && (p0 < 0 || !((((p0 & 1) ? pm1 : pm0) >> (p0 >> 1)) & 1u));
-                                const bool r1 = mine1 && (p1 < 0 || !((((p1 & 1) ? pm1 : pm0) >> (p1 >> 1)) & 1u));
-                                if (r0) { dst[0] = bout[tag[2 * i]]; mine0 = false; }
-                                if (r1) { dst[1] = bout[tag[2 * i + 1]]; mine1 = false; }
-                                pm0 &= ~__ballot_sync(0xffffffffu, r0);
-                                pm1 &= ~__ballot_sync(0xffffffffu, r1);
+                                bool ready = mine && (tag[i] < row0 || !((pending >> (tag[i] - row0)) & 1u));
+                                if (ready) { bout[row0 + (int32_t)lane] = bout[tag[i]]; mine = false; }
+                                pending &= ~__ballot_sync(0xffffffffu, ready);
                             }
                         }
                     }
