@@ -884,7 +884,8 @@ __device__ __forceinline__ uint32_t exec_wait_progress(const BlockAux *aux, uint
 
 constexpr uint32_t EXEC_WARPS = 4;
 constexpr uint32_t EXEC_MAX_RUN = 127;                      // longest literal run / match the fast path takes
-constexpr uint32_t EXEC_MASK_WORDS = (32 * 2 * EXEC_MAX_RUN + 31) / 32 + 4;
+constexpr uint32_t EXEC_CHUNK_ROWS = 4;                    // rows (of 32 bytes) whose loads are in flight together
+constexpr uint32_t EXEC_MASK_WORDS = (32 * 2 * EXEC_MAX_RUN + 31) / 32 + EXEC_CHUNK_ROWS;
 
 __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__restrict__ descs, const BlockAux *__restrict__ aux,
                                                         const FrameDesc *__restrict__ frames, FrameState *__restrict__ states,
@@ -1011,7 +1012,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
                 const uint32_t lit_begin = m_start - my_ll;
                 const uint32_t l_start = st.litpos + lit_end - my_ll;  // literal index of my literal run
                 const uint32_t nrows = (T + 31) >> 5;
-                for (uint32_t w = lane; w < ((nrows + 3u) & ~3u); w += 32) mask[w] = 0;
+                for (uint32_t w = lane; w < ((nrows + EXEC_CHUNK_ROWS - 1u) & ~(EXEC_CHUNK_ROWS - 1u)); w += 32) mask[w] = 0;
                 recs[lane] = make_uint4(lit_begin | (m_start << 16), my_off, l_start, 0);
                 __syncwarp();
                 if (lane < nb) atomicOr(&mask[(out_end - 1) >> 5], 1u << ((out_end - 1) & 31u));
@@ -1023,14 +1024,14 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
                 // rows are produced four at a time: every byte whose source lies before the chunk (literals, and
                 // matches reaching back past the chunk start) is loaded first -- up to 4 independent loads per lane
                 // in flight -- then stored; the few bytes whose source lies inside the chunk follow, row by row.
-                for (uint32_t r0 = 0; r0 < nrows; r0 += 4) {
+                for (uint32_t r0 = 0; r0 < nrows; r0 += EXEC_CHUNK_ROWS) {
                     const int32_t chunk0 = (int32_t)(r0 << 5);
                     // tag: TAG_NONE = nothing to do, TAG_STORE = value loaded in phase 1, otherwise the (batch-relative,
                     // >= chunk0) source position of a match byte that depends on this chunk
                     constexpr int32_t TAG_NONE = INT32_MIN, TAG_STORE = INT32_MIN + 1;
-                    uint32_t val[4]; int32_t tag[4];
+                    uint32_t val[EXEC_CHUNK_ROWS]; int32_t tag[EXEC_CHUNK_ROWS];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
+                    for (int i = 0; i < (int)EXEC_CHUNK_ROWS; i++) {
                         const uint32_t q = ((r0 + i) << 5) + lane;
                         const uint32_t word = mask[r0 + i];
                         const uint32_t owner = before + __popc(word & lt);   // sequences that ended below q
@@ -1052,12 +1053,15 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
                         }
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; i++)
+                    for (int i = 0; i < (int)EXEC_CHUNK_ROWS; i++)
                         if (tag[i] == TAG_STORE) bout[((r0 + i) << 5) + lane] = (uint8_t)val[i];
                     // dependent bytes (source inside this chunk), rows in order
-                    if (__any_sync(0xffffffffu, (tag[0] >= chunk0) | (tag[1] >= chunk0) | (tag[2] >= chunk0) | (tag[3] >= chunk0))) {
+                    bool anydep = false;
 #pragma unroll
-                        for (int i = 0; i < 4; i++) {
+                    for (int i = 0; i < (int)EXEC_CHUNK_ROWS; i++) anydep |= tag[i] >= chunk0;
+                    if (__any_sync(0xffffffffu, anydep)) {
+#pragma unroll
+                        for (int i = 0; i < (int)EXEC_CHUNK_ROWS; i++) {
                             bool mine = tag[i] >= chunk0;
                             uint32_t pending = __ballot_sync(0xffffffffu, mine);
                             const int32_t row0 = chunk0 + (i << 5);
