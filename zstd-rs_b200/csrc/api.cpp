@@ -636,6 +636,9 @@ extern "C" void b200z_batch_destroy(b200z_batch *b) {
 // ---------------------------------------------------------------------------------------------------------------
 struct PipeResources {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    // chunk i's kernels run on stream pair i & 1, so the (latency-bound) kernels of neighbouring chunks overlap
+    cudaStream_t k_main[2] = {nullptr, nullptr}, k_side[2] = {nullptr, nullptr};
+    cudaEvent_t k_fork[2] = {nullptr, nullptr}, k_join[2] = {nullptr, nullptr};
     b200z_batch *set[2] = {nullptr, nullptr};
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     FrameState *h_states[2] = {nullptr, nullptr};   // pinned
@@ -652,6 +655,10 @@ static void pipe_free(b200z_ctx *c) {
         if (p->ev_h2d[i]) cudaEventDestroy(p->ev_h2d[i]);
         if (p->ev_k[i]) cudaEventDestroy(p->ev_k[i]);
         if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]);
+        if (p->k_fork[i]) cudaEventDestroy(p->k_fork[i]);
+        if (p->k_join[i]) cudaEventDestroy(p->k_join[i]);
+        if (p->k_main[i]) cudaStreamDestroy(p->k_main[i]);
+        if (p->k_side[i]) cudaStreamDestroy(p->k_side[i]);
         if (p->h_states[i]) cudaFreeHost(p->h_states[i]);
     }
     if (p->s_h2d) cudaStreamDestroy(p->s_h2d);
@@ -665,7 +672,13 @@ static int pipe_get(b200z_ctx *c, PipeResources **out) {
         std::unique_ptr<PipeResources> p(new PipeResources());
         CU(c, cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
         CU(c, cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         for (int i = 0; i < 2; i++) {
+            CU(c, cudaStreamCreateWithPriority(&p->k_main[i], cudaStreamNonBlocking, prio_hi));
+            CU(c, cudaStreamCreateWithPriority(&p->k_side[i], cudaStreamNonBlocking, prio_lo));
+            CU(c, cudaEventCreateWithFlags(&p->k_fork[i], cudaEventDisableTiming));
+            CU(c, cudaEventCreateWithFlags(&p->k_join[i], cudaEventDisableTiming));
             p->set[i] = new b200z_batch();
             p->set[i]->ctx = c;
             CU(c, cudaEventCreateWithFlags(&p->ev_h2d[i], cudaEventDisableTiming));
@@ -729,19 +742,20 @@ static int decode_frames_pipelined(b200z_ctx *c, const uint8_t *input, size_t in
         if (ihi > ilo) CU(c, cudaMemcpyAsync(p->d_in[s].p, input + ilo, ihi - ilo, cudaMemcpyHostToDevice, p->s_h2d));
         if (int e = b->sub.upload(c, p->s_h2d)) return e;
         CU(c, cudaEventRecord(p->ev_h2d[s], p->s_h2d));
-        CU(c, cudaStreamWaitEvent(c->stream, p->ev_h2d[s], 0));
+        cudaStream_t km = p->k_main[s];
+        CU(c, cudaStreamWaitEvent(km, p->ev_h2d[s], 0));
         PipelineArgs a = b->sub.args(p->d_in[s].as<uint8_t>() - ilo, d_out, output_cap);
-        PipelineStreams ps{c->stream, c->side, c->ev_fork, c->ev_join};
+        PipelineStreams ps{km, p->k_side[s], p->k_fork[s], p->k_join[s]};
         int le = launch_pipeline_overlapped(a, ps);
         if (le) return c->set_cuda_err((cudaError_t)le, "launch_pipeline");
         c->launches += pipeline_launch_count(a);
         b->checksummed = false;
         if ((c->flags & B200Z_FLAG_CHECKSUM) && a.nframes) {
-            if ((le = launch_checksum(a, c->stream))) return c->set_cuda_err((cudaError_t)le, "launch_checksum");
+            if ((le = launch_checksum(a, km))) return c->set_cuda_err((cudaError_t)le, "launch_checksum");
             c->launches += 1;
             b->checksummed = true;
         }
-        CU(c, cudaEventRecord(p->ev_k[s], c->stream));
+        CU(c, cudaEventRecord(p->ev_k[s], km));
         CU(c, cudaStreamWaitEvent(p->s_d2h, p->ev_k[s], 0));
         size_t nst = b->sub.states.size();
         if (nst > p->h_states_cap[s]) {
