@@ -375,6 +375,50 @@ def test_pipelined_one_shot_many_chunks(pkg, ctx, monkeypatch):
     assert (res["status"][ok] == 0).all()
 
 
+def test_irregular_huffman_split_matches_reference_semantics(pkg, ctx, oracle):
+    """ruzstd derives the 4 literal stream sizes from bit exhaustion, not from (n+3)/4, and only checks the total.
+    A frame with an uneven split is rejected by libzstd but decodes under the reference's rules; the GPU fast path must notice and
+    replay the block exactly.  Also: the same frame with one stream truncated must fail with the oracle's error."""
+    import craft
+    import datagen as G
+    zo, bz = oracle.error_names(), pkg.error_names()
+    for seed, shift in [(77, 7), (78, 1), (79, 250)]:
+        text = G.gen_text(60000, seed)
+        frame, plain = craft.irregular_huffman_split(oracle, G.compress(text), shift=shift)
+        with pytest.raises(RuntimeError):
+            G.decompress(frame, len(plain))            # the stock decoder refuses it
+        exp, _ = oracle.decode_frame(frame)
+        assert exp == plain
+        out = np.zeros(len(plain) + 16, dtype=np.uint8)
+        io = np.zeros(1, dtype=pkg.binding.FRAME_IO_DTYPE); io[0] = (0, len(frame), 0, len(plain))
+        res = pkg.decode_frames(ctx, np.frombuffer(frame, dtype=np.uint8), io, out)
+        assert res[0]["status"] == 0 and out[:len(plain)].tobytes() == plain
+        dec = pkg.FrameDecoder(ctx)
+        r = dec.reset(frame); dec.decode_blocks(r, pkg.ALL)
+        assert dec.collect() == plain and dec.get_calculated_checksum() == dec.get_checksum_from_data()
+        # corrupt the jump table: stream 1 one byte shorter, stream 2 one byte longer -> same error as the oracle
+        bad = bytearray(frame)
+        pos = frame.index(frame[:4]) + 0
+        hdr_end, _ = craft._parse_single_block(frame)
+        # literals header is 5 bytes (size format 3); jump table follows the tree description
+        lit0 = hdr_end + 3 + 5
+        tree = bad[lit0]
+        tlen = 1 + (tree if tree < 128 else (tree - 127 + 1) // 2)
+        j = lit0 + tlen
+        v = int.from_bytes(bad[j:j + 2], "little") - 1
+        bad[j:j + 2] = v.to_bytes(2, "little")
+        bad = bytes(bad)
+        try:
+            e_out, _ = oracle.decode_frame(bad); e_err = None
+        except oracle.OracleError as e:
+            e_out, e_err = None, (zo[e.code].replace("ZO_", ""), e.stage)
+        res = pkg.decode_frames(ctx, np.frombuffer(bad, dtype=np.uint8), io, out)
+        if e_err is None:
+            assert res[0]["status"] == 0 and out[:res[0]["out_size"]].tobytes() == e_out
+        else:
+            assert (bz[int(res[0]["status"])].replace("B200Z_", ""), int(res[0]["stage"])) == e_err
+
+
 def test_target_too_small_and_capacity_isolation(pkg, ctx):
     """A frame that does not fit its out_cap fails alone and never writes past its slot (checked on the device buffer)."""
     import torch

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <memory>
 #include <string>
@@ -710,6 +711,9 @@ static int decode_frames_pipelined(b200z_ctx *c, const uint8_t *input, size_t in
         }
         cut.push_back(nframes);
     }
+    const bool trace = getenv("B200Z_TRACE") != nullptr;
+    auto t_start = std::chrono::steady_clock::now();
+    auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     struct Pending { size_t f0 = 0, f1 = 0; bool live = false; } pend[2];
     auto retire = [&](int s) -> int {   // results of the chunk that used set s
         if (!pend[s].live) return 0;
@@ -725,9 +729,12 @@ static int decode_frames_pipelined(b200z_ctx *c, const uint8_t *input, size_t in
     for (size_t ci = 0; ci + 1 < cut.size(); ci++) {
         const int s = (int)(ci & 1);
         const size_t f0 = cut[ci], f1 = cut[ci + 1];
+        double t0 = now_ms();
         if (int e = retire(s)) return e;
+        double t1 = now_ms();
         b200z_batch *b = p->set[s];
         if (int e = plan_batch(b, input, input_len, frames + f0, f1 - f0, dicts, ndicts, forced, max_window)) return e;
+        double t2 = now_ms();
         // input byte range and output byte range of this chunk
         uint64_t ilo = UINT64_MAX, ihi = 0, olo = UINT64_MAX, ohi = 0;
         for (size_t i = f0; i < f1; i++) {
@@ -768,9 +775,11 @@ static int decode_frames_pipelined(b200z_ctx *c, const uint8_t *input, size_t in
         if (ohi > olo) CU(c, cudaMemcpyAsync(output + olo, d_out + olo, ohi - olo, cudaMemcpyDeviceToHost, p->s_d2h));
         CU(c, cudaEventRecord(p->ev_done[s], p->s_d2h));
         pend[s].f0 = f0; pend[s].f1 = f1; pend[s].live = true;
+        if (trace) fprintf(stderr, "[b200z] chunk %zu frames %zu..%zu: start %.2f retire-wait %.2f plan %.2f enqueue %.2f ms\n", ci, f0, f1, t0, t1 - t0, t2 - t1, now_ms() - t2);
     }
     if (int e = retire(0)) return e;
     if (int e = retire(1)) return e;
+    if (trace) fprintf(stderr, "[b200z] pipelined one-shot done at %.2f ms\n", now_ms());
     return 0;
 }
 

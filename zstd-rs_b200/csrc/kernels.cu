@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(const BlockDesc *__r
         if (d.lit_type == LT_COMPRESSED) {
             uint32_t used = 0, nweights = 0;
             int e = 0;
-            if (lane == 0) e = huf_read_weights(content + d.lit_off, d.lit_comp_size, sc.weights, nweights, used);
+            if (lane == 0) e = huf_read_weights_scratch(content + d.lit_off, d.lit_comp_size, sc.weights, nweights, used, sc.probs, sc.wtab, sc.wcount);
             e = __shfl_sync(0xffffffffu, e, 0);
             used = __shfl_sync(0xffffffffu, used, 0); nweights = __shfl_sync(0xffffffffu, nweights, 0);
             __syncwarp();

@@ -23,6 +23,8 @@ struct alignas(16) SetupScratch {  // per warp, shared memory
     uint8_t cell_sym[FSE_MAX_ENTRIES];
     uint16_t count[64];
     uint16_t start[264];           // Huffman: first table index of each symbol
+    uint32_t wtab[64];             // FSE table of the compressed Huffman weights (lane 0)
+    uint16_t wcount[256];          // its state counters
 };
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }

@@ -114,7 +114,8 @@ B200Z_HDN inline int fse_read_probabilities(const uint8_t *src, uint32_t len, ui
 
 // build_decoding_table into packed entries.  `out` may be global memory; it is used as its own scratch
 // (pass 1 stores the symbol, pass 2 rewrites each entry with base_line/num_bits).
-B200Z_HDN inline int fse_build_table(const int16_t *probs, uint32_t nprobs, uint32_t acc_log, uint32_t max_symbol, uint32_t *out) {
+// `counter` = scratch for 256 u16 (callers on the GPU pass shared memory: per-thread local arrays of this size spill to L2)
+B200Z_HDN inline int fse_build_table(const int16_t *probs, uint32_t nprobs, uint32_t acc_log, uint32_t max_symbol, uint32_t *out, uint16_t *counter) {
     if (nprobs > max_symbol + 1) return B200Z_ERR_FSE_TOO_MANY_SYMBOLS;
     const uint32_t size = 1u << acc_log;
     uint32_t negative_idx = size;
@@ -138,7 +139,6 @@ B200Z_HDN inline int fse_build_table(const int16_t *probs, uint32_t nprobs, uint
             }
         }
     }
-    uint16_t counter[256];
     for (uint32_t s = 0; s < nprobs && s < 256; s++) counter[s] = 0;
     for (uint32_t i = 0; i < negative_idx; i++) {
         uint32_t sym = out[i] & 0xffu;  // unwritten entries read as whatever pass 1 left: all get written when sum == size
@@ -173,7 +173,8 @@ B200Z_HDN inline int fse_build_decoder(const uint8_t *src, uint32_t len, uint32_
     int e = fse_read_probabilities(src, len, max_log, max_symbol, probs, nprobs, acc_log, bytes_read);
     if (e) return e;
     uint32_t wide[FSE_MAX_ENTRIES];
-    e = fse_build_table(probs, nprobs, acc_log, max_symbol, wide);
+    uint16_t counter[256];
+    e = fse_build_table(probs, nprobs, acc_log, max_symbol, wide, counter);
     if (e) return e;
     fse_compact(wide, acc_log, tab);
     return 0;
@@ -190,7 +191,8 @@ B200Z_HDN inline int fse_build_predefined(uint32_t kind /*0 ll,1 of,2 ml*/, FseT
     else if (kind == 1) { n = 29; log = 5; maxsym = 31; for (uint32_t i = 0; i < n; i++) probs[i] = OF[i]; }
     else { n = 53; log = 6; maxsym = 52; for (uint32_t i = 0; i < n; i++) probs[i] = ML[i]; }
     uint32_t wide[64];
-    int e = fse_build_table(probs, n, log, maxsym, wide);
+    uint16_t counter[64];
+    int e = fse_build_table(probs, n, log, maxsym, wide, counter);
     if (e) return e;
     fse_compact(wide, log, tab);
     return 0;
@@ -198,7 +200,9 @@ B200Z_HDN inline int fse_build_predefined(uint32_t kind /*0 ll,1 of,2 ml*/, FseT
 
 // ---- Huffman ----------------------------------------------------------------------------------------------
 // read_weights: weights[] (capacity 260), nweights, bytes_read.
-B200Z_HDN inline int huf_read_weights(const uint8_t *src, uint32_t len, uint8_t *weights, uint32_t &nweights, uint32_t &bytes_read) {
+// probs[256], tab[64], counter[256]: scratch (shared memory on the GPU)
+B200Z_HDN inline int huf_read_weights_scratch(const uint8_t *src, uint32_t len, uint8_t *weights, uint32_t &nweights, uint32_t &bytes_read,
+                                              int16_t *probs, uint32_t *tab, uint16_t *counter) {
     if (len == 0) return B200Z_ERR_HUF_SOURCE_IS_EMPTY;
     const uint32_t header = src[0];
     uint32_t bits_read = 8;
@@ -206,12 +210,10 @@ B200Z_HDN inline int huf_read_weights(const uint8_t *src, uint32_t len, uint8_t 
         const uint8_t *fs = src + 1;
         const uint32_t fs_len = len - 1;
         if (header > fs_len) return B200Z_ERR_HUF_NOT_ENOUGH_BYTES_FOR_WEIGHTS;
-        int16_t probs[256];
         uint32_t nprobs, acc_log, used;
         int e = fse_read_probabilities(fs, fs_len, 6, 255, probs, nprobs, acc_log, used);
         if (e) return e;
-        uint32_t tab[64];
-        e = fse_build_table(probs, nprobs, acc_log, 255, tab);
+        e = fse_build_table(probs, nprobs, acc_log, 255, tab, counter);
         if (e) return e;
         if (used > header) return B200Z_ERR_HUF_FSE_TABLE_USED_TOO_MANY_BYTES;
         const uint32_t clen = header - used;
@@ -246,6 +248,13 @@ B200Z_HDN inline int huf_read_weights(const uint8_t *src, uint32_t len, uint8_t 
     }
     bytes_read = (bits_read + 7u) >> 3;
     return 0;
+}
+
+B200Z_HDN inline int huf_read_weights(const uint8_t *src, uint32_t len, uint8_t *weights, uint32_t &nweights, uint32_t &bytes_read) {
+    int16_t probs[256];
+    uint32_t tab[64];
+    uint16_t counter[256];
+    return huf_read_weights_scratch(src, len, weights, nweights, bytes_read, probs, tab, counter);
 }
 
 // build_table_from_weights into a HufSlot (serial form: dictionaries on the host; the per-block GPU form is in setup.cuh)
