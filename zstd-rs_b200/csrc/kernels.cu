@@ -174,6 +174,7 @@ constexpr uint32_t HUF_SMEM_PER_BLOCK = HUF_TABLE_ENTRIES + HUF_TABLE_ENTRIES / 
 __device__ __forceinline__ uint32_t shr_c(uint32_t a, uint32_t n) { uint32_t r; asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(n)); return r; }
 __device__ __forceinline__ uint32_t shl_c(uint32_t a, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(n)); return r; }
 __device__ __forceinline__ uint32_t fsl_c(uint32_t lo, uint32_t hi, uint32_t n) { return __funnelshift_lc(lo, hi, n); }
+__device__ __forceinline__ uint32_t bfind32(uint32_t a) { uint32_t r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(a)); return r; }   // floor(log2 a)
 
 // Reversed bit reader whose words come from a per-lane ring in shared memory (32 words = 8 groups of 16 bytes)
 // that cp.async keeps filled 7 groups ahead of consumption: the refill is two shifts and an LDS, never a global
@@ -258,6 +259,67 @@ struct RingBits {
         lo = shl_c(lo, n);
         fill -= (int32_t)n;
         p -= (int32_t)n;
+    }
+};
+
+// Position-based reversed bit reader for k_fse's fast path.  The only state is P = bits_remaining()
+// (bit_reader_reverse.rs:27-29); every read assembles the 64 bits below position P from three words of a per-lane
+// shared-memory ring (8 groups of 16 bytes + a mirror of the top group below slot 0, so that the three words are
+// always at a0, a0 - 4, a0 - 8) that cp.async keeps filled 7 groups ahead of consumption.  No window registers,
+// no refill / skip bookkeeping: a step costs 3 LDS + 2 funnel shifts.  Bits below the stream start are NOT
+// zeroed here: reading them makes P negative, which the caller checks (the block is then replayed by the exact
+// path, whose reader zero-fills like BitReaderReversed, bit_reader_reverse.rs:57-83).
+struct PosRing {
+    const uint4 *base;   // 16-byte aligned address at or below the stream start
+    uint32_t ring;       // shared-memory byte address of slot 0 (the mirror slot is at ring - 16)
+    int32_t gm1;         // bit offset of the stream's first byte inside group 0, minus 1
+    int32_t next_g;      // next group to request (descending)
+    int32_t P;           // bits_remaining()
+
+    __device__ __forceinline__ uint32_t lds(uint32_t addr) const { uint32_t w; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr) : "memory"); return w; }
+    // request group g when `on` (predicated, no branch): slot g & 7, plus the mirror below slot 0 for slot 7
+    __device__ __forceinline__ void request(int32_t g, bool on) {
+        const uint32_t slot = (uint32_t)g & 7u;
+        const uint32_t dst = ring + (slot << 4);
+        const uint4 *src = base + g;
+        const uint32_t p1 = on ? 1u : 0u, p2 = (on && slot == 7u) ? 1u : 0u;
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %3, 0;\n\tsetp.ne.u32 q, %4, 0;\n\t"
+                     "@p cp.async.cg.shared.global [%0], [%2], 16;\n\t@q cp.async.cg.shared.global [%1], [%2], 16;\n\t"
+                     "cp.async.commit_group;\n\t}" ::"r"(dst), "r"(ring - 16u), "l"(src), "r"(p1), "r"(p2) : "memory");
+    }
+    __device__ __forceinline__ bool init(const uint8_t *src, uint32_t len, uint32_t ring_slot0) {
+        ring = ring_slot0; base = nullptr; gm1 = -1; next_g = -1; P = 0;
+        if (len == 0) return false;
+        const uint32_t last = src[len - 1];
+        if (last == 0) return false;
+        const uintptr_t a = (uintptr_t)src;
+        base = (const uint4 *)(a & ~(uintptr_t)15);
+        gm1 = (int32_t)((uint32_t)(a & 15) * 8u) - 1;
+        P = (int32_t)((len - 1) * 8u + (31u - (uint32_t)__clz((int)last)));
+        const int32_t gt = (gm1 + P) >> 7;    // group of the first data bit (-1 only for an empty stream at offset 0)
+        for (int32_t g = gt; g > gt - 8; g--) request(g, g >= 0);
+        next_g = gt - 8;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        return true;
+    }
+    // the 64 bits below position P, left aligned in hi:lo (garbage once P < 64 bits from the stream start: unused)
+    __device__ __forceinline__ void window(uint32_t &hi, uint32_t &lo) const {
+        const int32_t G = gm1 + P;                               // bit index (from `base`) of the next unread bit
+        const uint32_t a0 = ring + (((uint32_t)G >> 3) & 0x7cu);  // word (G >> 5) & 31 of the ring
+        const uint32_t A = lds(a0), B = lds(a0 - 4u), C = lds(a0 - 8u);
+        const uint32_t sh = ~(uint32_t)G;                         // 31 - (G & 31), the funnel shift uses the low 5 bits
+        hi = __funnelshift_l(B, A, sh);
+        lo = __funnelshift_l(C, B, sh);
+    }
+    // Keeps the ring 7 groups ahead.  Call at least once per 116 consumed bits (every second sequence): consumption
+    // then leaves at most one group per call, so one request per call keeps up; the groups a step can touch before
+    // the next call (down to 2 below the current one) are complete after wait_group 5.
+    __device__ __forceinline__ void service() {
+        const int32_t gh = (gm1 + P) >> 7;
+        const bool need = next_g >= gh - 7;
+        request(next_g, need && next_g >= 0);
+        next_g -= need ? 1 : 0;
+        asm volatile("cp.async.wait_group 5;" ::: "memory");
     }
 };
 
@@ -614,65 +676,83 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
         const uint8_t *src = input + d->src_off + aux[b].seq_bits_off;
         const uint32_t len = d->src_size - aux[b].seq_bits_off;
         const uint16_t *TL = tabs + lane * FSE_TAB_U16, *TM = TL + 512, *TO = TL + 1024;
-        RingBits br;
-        uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(s_ring + lane * RING_STRIDE);
+        PosRing br;
+        const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(s_ring + lane * RING_STRIDE) + 16u;   // slot 0; the mirror slot sits below
         bool bad = !br.init(src, len, ring_addr) || !tl || !tl->valid || !to || !to->valid || !tm || !tm->valid;
         if (!bad) {
             const uint32_t logL = tl->log, logM = tm->log, logO = to->log;
+            // table byte addresses in shared memory, biased by -2^log entries: the next state is (f << nb) + bits - 2^log
+            const uint32_t aTL = (uint32_t)__cvta_generic_to_shared(TL), aTM = (uint32_t)__cvta_generic_to_shared(TM), aTO = (uint32_t)__cvta_generic_to_shared(TO);
+            const uint32_t pTL = aTL - (2u << logL), pTM = aTM - (2u << logM), pTO = aTO - (2u << logO);
+            const uint32_t aLL = (uint32_t)__cvta_generic_to_shared(s_ll), aML = (uint32_t)__cvta_generic_to_shared(s_ml);
+            auto lds16 = [](uint32_t addr) -> uint32_t { uint16_t w; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(w) : "r"(addr) : "memory"); return w; };
             uint32_t eL, eM, eO;
-            br.refill(); eL = TL[shr_c(br.hi, 32u - logL)]; br.skip(logL);
-            br.refill(); eO = TO[shr_c(br.hi, 32u - logO)]; br.skip(logO);
-            br.refill(); eM = TM[shr_c(br.hi, 32u - logM)]; br.skip(logM);
+            {   // initial states LL, OF, ML (sequence_section_decoder.rs:164-166)
+                uint32_t hi, lo;
+                br.window(hi, lo);
+                const uint32_t t1 = shl_c(hi, logL), t2 = shl_c(t1, logO);
+                eL = lds16(aTL + (shr_c(hi, 32u - logL) << 1));
+                eO = lds16(aTO + (shr_c(t1, 32u - logO) << 1));
+                eM = lds16(aTM + (shr_c(t2, 32u - logM) << 1));
+                br.P -= (int32_t)(logL + logO + logM);
+            }
             uint32_t *out = seq_scratch + d->seq_buf_off * 3;
             const uint32_t nseq = d->nseq;
             const bool resolve = d->fse_resolves != 0;
             uint32_t h0 = d->init_hist[0], h1 = d->init_hist[1], h2 = d->init_hist[2];
             uint64_t sum_ml = 0;
-            uint32_t flags = 0;
+            uint32_t flags = 0, or_of = 0, max_x = 0;
             uint32_t stage[12];
+            uint32_t qTL = pTL, qTM = pTM, qTO = pTO, qLL = aLL, qML = aML;
+            asm volatile("" : "+r"(qTL), "+r"(qTM), "+r"(qTO), "+r"(qLL), "+r"(qML));   // keep the five table addresses in registers
             auto step = [&](uint32_t &o_ll, uint32_t &o_ml, uint32_t &o_of, bool update) {
+                uint32_t hi, lo;
+                br.window(hi, lo);
                 const uint32_t cL = eL >> 10, cM = eM >> 10, cO = eO >> 10;
-                const uint32_t vL = s_ll[cL], vM = s_ml[cM];   // base | extra_bits << 24; codes are < 64 and the two LUTs are adjacent (89 entries + pad)
+                const uint32_t vL = br.lds(qLL + (cL << 2)), vM = br.lds(qML + (cM << 2));   // base | extra_bits << 24
                 const uint32_t xL = vL >> 24, xM = vM >> 24, xO = cO;
-                flags |= (cO >> 5);   // offset code > 31 (LL/ML codes are capped by table construction, scratch.rs:36-40)
-                // state transitions out of the compact entries (b200z_types.h): nb = log - floor(log2 f), base = (f - 2^h) << nb
-                const uint32_t fL = eL & 1023u, fM = eM & 1023u, fO = eO & 1023u;
-                const uint32_t hL = 31u - (uint32_t)__clz((int)fL), hM = 31u - (uint32_t)__clz((int)fM), hO = 31u - (uint32_t)__clz((int)fO);
-                const uint32_t nbL = logL - hL, nbM = logM - hM, nbO = logO - hO;
-                const uint32_t bL = (fL ^ (1u << hL)) << nbL, bM = (fM ^ (1u << hM)) << nbM, bO = (fO ^ (1u << hO)) << nbO;
+                or_of |= cO;          // offset code > 31 is checked per group (LL/ML codes are capped by table construction, scratch.rs:36-40)
                 // extra bits: OF, ML, LL (get_bits_triple, sequence_section_decoder.rs:185)
-                br.refill();
                 const uint32_t xsum = xO + xM + xL;
-                flags |= (xsum > 32u);
-                const uint32_t t0 = br.hi, t1 = shl_c(t0, xO), t2 = shl_c(t1, xM);
-                const uint32_t obits = shr_c(t0, 32u - xO), ml_add = shr_c(t1, 32u - xM), ll_add = shr_c(t2, 32u - xL);
-                br.skip(xsum > 32u ? 32u : xsum);
+                max_x = max(max_x, xsum);   // > 32 extra bits in one sequence: not for this path, checked per group
+                const uint32_t t1 = shl_c(hi, xO), t2 = shl_c(t1, xM);
+                const uint32_t obits = shr_c(hi, 32u - xO), ml_add = shr_c(t1, 32u - xM), ll_add = shr_c(t2, 32u - xL);
                 uint32_t offset = obits + (1u << (cO & 31u));
                 const uint32_t ll = (vL & 0xFFFFFFu) + ll_add, ml = (vM & 0xFFFFFFu) + ml_add;
                 sum_ml += ml;
-                if (resolve) {   // do_offset_history (sequence_execution.rs:59-118) with selects
-                    const uint32_t kk = offset > 3u ? 4u : offset - 1u + (ll == 0u ? 1u : 0u);
-                    const uint32_t h0m1 = h0 ? h0 - 1u : 0u;
-                    const uint32_t actual = kk == 0u ? h0 : (kk == 1u ? h1 : (kk == 2u ? h2 : (kk == 3u ? h0m1 : offset - 3u)));
-                    h2 = kk <= 1u ? h2 : h1;
-                    h1 = kk == 0u ? h1 : h0;
+                {   // do_offset_history (sequence_execution.rs:59-118), branch-free; the result is used only when `resolve`
+                    const bool rep = offset <= 3u;
+                    const uint32_t r = offset - 1u + (ll == 0u ? 1u : 0u);   // 0..3 when rep
+                    const uint32_t h0m1 = h0 - (h0 != 0u ? 1u : 0u);          // saturating_sub (:74)
+                    uint32_t cand = h0;
+                    cand = r == 1u ? h1 : cand;
+                    cand = r == 2u ? h2 : cand;
+                    cand = r == 3u ? h0m1 : cand;
+                    const uint32_t actual = rep ? cand : offset - 3u;
+                    const bool keep2 = rep && r <= 1u, keep1 = rep && r == 0u;
+                    h2 = keep2 ? h2 : h1;
+                    h1 = keep1 ? h1 : h0;
                     h0 = actual;
-                    offset = actual;
+                    offset = resolve ? actual : offset;
                 }
                 o_ll = ll; o_ml = ml; o_of = offset;
-                if (update) {   // state updates LL, ML, OF (:198-207)
-                    br.refill();
-                    const uint32_t u0 = br.hi, u1 = shl_c(u0, nbL), u2 = shl_c(u1, nbM);
+                if (update) {   // state updates LL, ML, OF (:198-207); compact entries (b200z_types.h): nb = log - floor(log2 f)
+                    const uint32_t fL = eL & 1023u, fM = eM & 1023u, fO = eO & 1023u;
+                    const uint32_t nbL = logL - bfind32(fL), nbM = logM - bfind32(fM), nbO = logO - bfind32(fO);
+                    const uint32_t u0 = fsl_c(lo, hi, xsum);                 // the 32 bits below the extra bits
+                    const uint32_t u1 = shl_c(u0, nbL), u2 = shl_c(u1, nbM);
                     const uint32_t aL = shr_c(u0, 32u - nbL), aM = shr_c(u1, 32u - nbM), aO = shr_c(u2, 32u - nbO);
-                    br.skip(nbL + nbM + nbO);
-                    eL = TL[bL + aL]; eM = TM[bM + aM]; eO = TO[bO + aO];
-                }
+                    eL = lds16(qTL + (((fL << nbL) + aL) << 1));
+                    eM = lds16(qTM + (((fM << nbM) + aM) << 1));
+                    eO = lds16(qTO + (((fO << nbO) + aO) << 1));
+                    br.P -= (int32_t)(xsum + nbL + nbM + nbO);
+                } else br.P -= (int32_t)xsum;
             };
             uint32_t i = 0;
             for (; i + 4 < nseq; i += 4) {
 #pragma unroll
                 for (int q = 0; q < 4; q++) { step(stage[3 * q], stage[3 * q + 1], stage[3 * q + 2], true); if (q & 1) br.service(); }
-                flags |= (uint32_t)(br.p < 0);   // bits_remaining only decreases: one check per group is equivalent
+                flags |= (uint32_t)(br.P < 0) | (uint32_t)(max_x > 32u) | (or_of >> 5);   // bits_remaining only decreases: one check per group is equivalent
                 uint4 *o4 = reinterpret_cast<uint4 *>(out + 3 * i);
                 o4[0] = make_uint4(stage[0], stage[1], stage[2], stage[3]);
                 o4[1] = make_uint4(stage[4], stage[5], stage[6], stage[7]);
@@ -685,11 +765,11 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
                     uint32_t ll, ml, of;
                     step(ll, ml, of, i + 1 < nseq);
                     br.service();
-                    flags |= (uint32_t)(br.p < 0);
+                    flags |= (uint32_t)(br.P < 0) | (uint32_t)(max_x > 32u) | (or_of >> 5);
                     out[3 * i] = ll; out[3 * i + 1] = ml; out[3 * i + 2] = of;
                 }
             }
-            bad = flags != 0 || br.p != 0;
+            bad = flags != 0 || br.P != 0;
             if (!bad) {
                 aux[b].pad = 0;
                 if (resolve) { aux[b].hist_after[0] = h0; aux[b].hist_after[1] = h1; aux[b].hist_after[2] = h2; }
@@ -893,12 +973,12 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
                                                         const uint32_t *__restrict__ seq_scratch, uint8_t *__restrict__ output, uint64_t output_cap,
                                                         uint32_t nframes) {
     __shared__ uint32_t s_mask[EXEC_WARPS][EXEC_MASK_WORDS];
-    __shared__ uint4 s_recs[EXEC_WARPS][32];
+    __shared__ uint2 s_recs[EXEC_WARPS][32];
     const uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31, lt = lanemask_lt();
     if (f >= nframes) return;
     uint32_t *mask = s_mask[threadIdx.x >> 5];
-    uint4 *recs = s_recs[threadIdx.x >> 5];
+    uint2 *recs = s_recs[threadIdx.x >> 5];
     const FrameDesc &fd = frames[f];
     FrameState fs = states[f];
     ExecState st;
@@ -1009,21 +1089,24 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
                 // the last byte of every sequence, so the owner of output byte q is the number of set bits below q;
                 // one 16-byte shared-memory record per sequence then tells the byte where it comes from.
                 const uint32_t m_start = out_end - my_ml;              // batch-relative start of my match
-                const uint32_t lit_begin = m_start - my_ll;
-                const uint32_t l_start = st.litpos + lit_end - my_ll;  // literal index of my literal run
+                const uint32_t m_before = m_start - lit_end;           // match bytes of the earlier sequences of the batch
                 const uint32_t nrows = (T + 31) >> 5;
                 for (uint32_t w = lane; w < ((nrows + EXEC_CHUNK_ROWS - 1u) & ~(EXEC_CHUNK_ROWS - 1u)); w += 32) mask[w] = 0;
-                recs[lane] = make_uint4(lit_begin | (m_start << 16), my_off, l_start, 0);
+                // 8-byte record: literal byte q of the sequence is literal number (q - m_before) of the batch, match byte q
+                // comes from output position q - offset (m_start <= 32 * 254, m_before <= 32 * 127: 16 bits each)
+                recs[lane] = make_uint2(m_start | (m_before << 16), my_off);
+                const bool has_ovl = __any_sync(0xffffffffu, my_off < my_ml);   // some match overlaps its own output (rare)
                 __syncwarp();
                 if (lane < nb) atomicOr(&mask[(out_end - 1) >> 5], 1u << ((out_end - 1) & 31u));
                 __syncwarp();
                 uint8_t *bout = out + st.produced;
-                const uint8_t *litp = lit.p;
-                asm volatile("" : "+l"(bout), "+l"(litp));   // keep both bases as single 64-bit registers (one add per access)
+                const uint8_t *litq = lit.p + st.litpos;
+                asm volatile("" : "+l"(bout), "+l"(litq));   // keep both bases as single 64-bit registers (one add per access)
                 uint32_t before = 0;   // sequences ended in earlier rows
                 // rows are produced four at a time: every byte whose source lies before the chunk (literals, and
                 // matches reaching back past the chunk start) is loaded first -- up to 4 independent loads per lane
                 // in flight -- then stored; the few bytes whose source lies inside the chunk follow, row by row.
+                // The per-byte work is branch-free: one select between the literal and the match source.
                 for (uint32_t r0 = 0; r0 < nrows; r0 += EXEC_CHUNK_ROWS) {
                     const int32_t chunk0 = (int32_t)(r0 << 5);
                     // tag: TAG_NONE = nothing to do, TAG_STORE = value loaded in phase 1, otherwise the (batch-relative,
@@ -1036,21 +1119,21 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
                         const uint32_t word = mask[r0 + i];
                         const uint32_t owner = before + __popc(word & lt);   // sequences that ended below q
                         before += __popc(word);
-                        const uint4 rc = recs[owner & 31u];
-                        const uint32_t mst = rc.x >> 16;
-                        tag[i] = TAG_NONE; val[i] = 0;
-                        if (q < T) {
-                            if (q < mst) {
-                                val[i] = litp[rc.z + (q - (rc.x & 0xffffu))];
-                                tag[i] = TAG_STORE;
-                            } else {
-                                uint32_t kk = q - mst;
-                                if (kk >= rc.y) kk %= rc.y;                  // overlapping match: byte k comes from k mod offset
-                                const int32_t sp = (int32_t)mst - (int32_t)rc.y + (int32_t)kk;   // batch-relative source
-                                tag[i] = sp;
-                                if (sp < chunk0) { val[i] = bout[sp]; tag[i] = TAG_STORE; }
-                            }
+                        const uint2 rc = recs[owner & 31u];
+                        const uint32_t mst = rc.x & 0xffffu;
+                        const bool is_match = q >= mst;
+                        int32_t sp = (int32_t)q - (int32_t)rc.y;                  // batch-relative source of a match byte
+                        if (has_ovl) {                                            // overlapping match: byte k comes from k mod offset
+                            const uint32_t kk = q - mst;
+                            if (is_match && kk >= rc.y) sp = (int32_t)mst - (int32_t)rc.y + (int32_t)(kk % rc.y);
                         }
+                        const bool valid = q < T;
+                        const bool dep = is_match && sp >= chunk0;
+                        const int32_t idx = is_match ? sp : (int32_t)(q - (rc.x >> 16));
+                        const uint8_t *bp = is_match ? (const uint8_t *)bout : litq;
+                        tag[i] = valid ? (dep ? sp : TAG_STORE) : TAG_NONE;
+                        val[i] = 0;
+                        if (valid && !dep) val[i] = bp[idx];
                     }
 #pragma unroll
                     for (int i = 0; i < (int)EXEC_CHUNK_ROWS; i++)
