@@ -941,6 +941,7 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -962,12 +963,26 @@ __device__ __forceinline__ uint32_t exec_wait_progress(const BlockAux *aux, uint
     return __shfl_sync(0xffffffffu, v, 0);
 }
 
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
+__device__ __forceinline__ void red_or_shared(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 constexpr uint32_t EXEC_WARPS = 4;
-constexpr uint32_t EXEC_MAX_RUN = 127;                      // longest literal run / match the fast path takes
-constexpr uint32_t EXEC_CHUNK_ROWS = 4;                    // rows (of 32 bytes) whose loads are in flight together
-constexpr uint32_t EXEC_MASK_WORDS = (32 * 2 * EXEC_MAX_RUN + 31) / 32 + EXEC_CHUNK_ROWS;
+constexpr uint32_t EXEC_TMAX = 8128;                        // most bytes one batch of 32 sequences may produce on the fast path
+#ifndef B200Z_EXEC_CHUNK_ROWS
+#define B200Z_EXEC_CHUNK_ROWS 4
+#endif
+#ifndef B200Z_EXEC_PREFETCH
+#define B200Z_EXEC_PREFETCH 1
+#endif
+constexpr uint32_t EXEC_CHUNK_ROWS = B200Z_EXEC_CHUNK_ROWS;                    // rows (of 32 bytes) whose loads are in flight together
+constexpr uint32_t EXEC_MASK_WORDS = (EXEC_TMAX + 31) / 32 + EXEC_CHUNK_ROWS;
+#ifndef B200Z_EXEC_MINB
+#define B200Z_EXEC_MINB 8
+#endif
 
-__global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__restrict__ descs, const BlockAux *__restrict__ aux,
+__global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const BlockDesc *__restrict__ descs, const BlockAux *__restrict__ aux,
                                                         const FrameDesc *__restrict__ frames, FrameState *__restrict__ states,
                                                         const uint8_t *__restrict__ input, const uint8_t *__restrict__ lit_scratch,
                                                         const uint32_t *__restrict__ seq_scratch, uint8_t *__restrict__ output, uint64_t output_cap,
@@ -977,8 +992,9 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
     const uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31, lt = lanemask_lt();
     if (f >= nframes) return;
-    uint32_t *mask = s_mask[threadIdx.x >> 5];
-    uint2 *recs = s_recs[threadIdx.x >> 5];
+    uint32_t a_mask = (uint32_t)__cvta_generic_to_shared(s_mask[threadIdx.x >> 5]);   // this warp's bitmask of sequence ends
+    uint32_t a_recs = (uint32_t)__cvta_generic_to_shared(s_recs[threadIdx.x >> 5]);   // this warp's per-sequence records
+    asm volatile("" : "+r"(a_mask), "+r"(a_recs));   // keep both addresses in registers (ptxas would recompute them from %tid per chunk)
     const FrameDesc &fd = frames[f];
     FrameState fs = states[f];
     ExecState st;
@@ -1070,15 +1086,15 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
                     }
                     // committed only if the fast path is taken (the exact path redoes the steps itself)
                     uint32_t m_start = out_end - my_ml;
-                    bool ok = lane >= nb || (my_ll <= EXEC_MAX_RUN && my_ml <= EXEC_MAX_RUN && my_off != 0 &&
+                    bool ok = lane >= nb || (my_off != 0 &&
                                              (uint64_t)my_off <= st.produced - st.drained + m_start);
-                    fast = __all_sync(0xffffffffu, ok) && (uint64_t)st.litpos + L <= lit.regen && st.produced + T <= st.cap && !lit.rle;
+                    fast = __all_sync(0xffffffffu, ok) && T <= EXEC_TMAX && (uint64_t)st.litpos + L <= lit.regen && st.produced + T <= st.cap && !lit.rle;
                     if (fast) { st.h0 = h0; st.h1 = h1; st.h2 = h2; }
                 } else {
                     uint32_t m_start = out_end - my_ml;
-                    bool ok = lane >= nb || (my_ll <= EXEC_MAX_RUN && my_ml <= EXEC_MAX_RUN && my_off != 0 &&
+                    bool ok = lane >= nb || (my_off != 0 &&
                                              (uint64_t)my_off <= st.produced - st.drained + m_start);
-                    fast = __all_sync(0xffffffffu, ok) && (uint64_t)st.litpos + L <= lit.regen && st.produced + T <= st.cap && !lit.rle;
+                    fast = __all_sync(0xffffffffu, ok) && T <= EXEC_TMAX && (uint64_t)st.litpos + L <= lit.regen && st.produced + T <= st.cap && !lit.rle;
                 }
                 if (!fast) {
                     e = exec_batch_exact(st, lit, fd, out, nb, my_ll, my_ml, my_of, resolved, lane);
@@ -1091,13 +1107,26 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
                 const uint32_t m_start = out_end - my_ml;              // batch-relative start of my match
                 const uint32_t m_before = m_start - lit_end;           // match bytes of the earlier sequences of the batch
                 const uint32_t nrows = (T + 31) >> 5;
-                for (uint32_t w = lane; w < ((nrows + EXEC_CHUNK_ROWS - 1u) & ~(EXEC_CHUNK_ROWS - 1u)); w += 32) mask[w] = 0;
+                // The batch's match sources are scattered over the frame's window, and with thousands of frames in flight the
+                // windows do not stay in L2: ask for the sectors now, a few hundred instructions before the rows need them.
+                if (!B200Z_EXEC_PREFETCH) {
+                } else if (lane < nb) {
+                    const uint8_t *src = out + st.produced + m_start - my_off;
+                    prefetch_l2(src);
+                    if ((((uint32_t)(uintptr_t)src) & 31u) + my_ml > 32u) prefetch_l2(src + my_ml - 1);
+                } else if (lane == 31) {
+                    const uint32_t ahead = st.litpos + L + 256u;   // the literal stream is sequential: stay two lines ahead
+                    prefetch_l2(lit.p + (ahead < lit.regen ? ahead : lit.regen - 1));
+                }
+                sts32(a_mask + (lane << 2), 0u);
+                if (nrows > 32u - EXEC_CHUNK_ROWS)
+                    for (uint32_t w = lane + 32; w < ((nrows + EXEC_CHUNK_ROWS - 1u) & ~(EXEC_CHUNK_ROWS - 1u)); w += 32) sts32(a_mask + (w << 2), 0u);
                 // 8-byte record: literal byte q of the sequence is literal number (q - m_before) of the batch, match byte q
                 // comes from output position q - offset (m_start <= 32 * 254, m_before <= 32 * 127: 16 bits each)
-                recs[lane] = make_uint2(m_start | (m_before << 16), my_off);
+                sts64(a_recs + (lane << 3), m_start | (m_before << 16), my_off);
                 const bool has_ovl = __any_sync(0xffffffffu, my_off < my_ml);   // some match overlaps its own output (rare)
                 __syncwarp();
-                if (lane < nb) atomicOr(&mask[(out_end - 1) >> 5], 1u << ((out_end - 1) & 31u));
+                if (lane < nb) red_or_shared(a_mask + (((out_end - 1) >> 5) << 2), 1u << ((out_end - 1) & 31u));
                 __syncwarp();
                 uint8_t *bout = out + st.produced;
                 const uint8_t *litq = lit.p + st.litpos;
@@ -1116,10 +1145,10 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 8) k_exec(const BlockDesc *__
 #pragma unroll
                     for (int i = 0; i < (int)EXEC_CHUNK_ROWS; i++) {
                         const uint32_t q = ((r0 + i) << 5) + lane;
-                        const uint32_t word = mask[r0 + i];
+                        const uint32_t word = lds32(a_mask + ((r0 + i) << 2));
                         const uint32_t owner = before + __popc(word & lt);   // sequences that ended below q
                         before += __popc(word);
-                        const uint2 rc = recs[owner & 31u];
+                        const uint2 rc = lds64(a_recs + ((owner & 31u) << 3));
                         const uint32_t mst = rc.x & 0xffffu;
                         const bool is_match = q >= mst;
                         int32_t sp = (int32_t)q - (int32_t)rc.y;                  // batch-relative source of a match byte
