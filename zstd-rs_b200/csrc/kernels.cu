@@ -965,13 +965,20 @@ __device__ __forceinline__ uint32_t exec_wait_progress(const BlockAux *aux, uint
 
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
 __device__ __forceinline__ void red_or_shared(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 constexpr uint32_t EXEC_WARPS = 4;
 constexpr uint32_t EXEC_TMAX = 8128;                        // most bytes one batch of 32 sequences may produce on the fast path
 #ifndef B200Z_EXEC_CHUNK_ROWS
 #define B200Z_EXEC_CHUNK_ROWS 4
+#endif
+#ifndef B200Z_EXEC_PIPE
+#define B200Z_EXEC_PIPE 0
 #endif
 #ifndef B200Z_EXEC_PREFETCH
 #define B200Z_EXEC_PREFETCH 1
@@ -1037,16 +1044,20 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
             else lit.p = lit_scratch + d.lit_buf_off;
             st.litpos = 0;
             uint32_t e = 0;
-            const bool resolved = d.fse_resolves != 0;
+            // block-level descriptor fields used inside the batch loop are consumed here once: a first use inside the loop
+            // would wait on a scoreboard shared with the record prefetch issued just before it (a full memory latency per batch)
+            uint32_t resolved_u = d.fse_resolves, nseq_u = d.nseq;
             const uint32_t *seqs = seq_scratch + d.seq_buf_off * 3;
+            asm volatile("" : "+r"(resolved_u), "+r"(nseq_u), "+l"(seqs));
+            const bool resolved = resolved_u != 0;
             __syncwarp();
             // sequence records stream in from k_fse, which may still be decoding this block: `avail` = published count.
             // Records are prefetched one batch ahead when they are already there.
             uint32_t avail = 0;
             uint32_t nx_ll = 0, nx_ml = 0, nx_of = 1;
             bool nx_loaded = false;
-            for (uint32_t base = 0; base < d.nseq && !e; base += 32) {
-                const uint32_t nb = d.nseq - base < 32 ? d.nseq - base : 32;
+            for (uint32_t base = 0; base < nseq_u && !e; base += 32) {
+                const uint32_t nb = nseq_u - base < 32 ? nseq_u - base : 32;
                 if (avail < base + nb) {
                     avail = exec_wait_progress(aux, b, base + nb, lane);
                     if (avail == 0xFFFFFFFEu) { e = B200Z_ERR_CUDA; break; }
@@ -1057,8 +1068,8 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                     if (lane < nb) { const uint32_t *s = seqs + (uint64_t)(base + lane) * 3; my_ll = ld_cg_u32(s); my_ml = ld_cg_u32(s + 1); my_of = ld_cg_u32(s + 2); }
                 }
                 nx_ll = 0; nx_ml = 0; nx_of = 1; nx_loaded = false;
-                if (base + 32 < d.nseq) {
-                    const uint32_t nb2 = d.nseq - base - 32 < 32 ? d.nseq - base - 32 : 32;
+                if (base + 32 < nseq_u) {
+                    const uint32_t nb2 = nseq_u - base - 32 < 32 ? nseq_u - base - 32 : 32;
                     if (avail < base + 32 + nb2) avail = ld_acquire_u32(&aux[b].progress);   // one look, no waiting
                     if (avail >= base + 32 + nb2) {
                         nx_loaded = true;
@@ -1132,18 +1143,18 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                 const uint8_t *litq = lit.p + st.litpos;
                 asm volatile("" : "+l"(bout), "+l"(litq));   // keep both bases as single 64-bit registers (one add per access)
                 uint32_t before = 0;   // sequences ended in earlier rows
-                // rows are produced four at a time: every byte whose source lies before the chunk (literals, and
-                // matches reaching back past the chunk start) is loaded first -- up to 4 independent loads per lane
-                // in flight -- then stored; the few bytes whose source lies inside the chunk follow, row by row.
+                // Rows are produced EXEC_CHUNK_ROWS at a time, software pipelined: the loads of chunk c + 1 (every byte whose
+                // source is final: literals, and matches reaching back past the start of chunk c) are issued before chunk c
+                // is stored, so their latency overlaps the stores and the next chunk's index work; the few bytes whose source
+                // lies inside the chunk being stored or the one in flight follow in the chunk's dependent phase, row by row.
                 // The per-byte work is branch-free: one select between the literal and the match source.
-                for (uint32_t r0 = 0; r0 < nrows; r0 += EXEC_CHUNK_ROWS) {
-                    const int32_t chunk0 = (int32_t)(r0 << 5);
-                    // tag: TAG_NONE = nothing to do, TAG_STORE = value loaded in phase 1, otherwise the (batch-relative,
-                    // >= chunk0) source position of a match byte that depends on this chunk
-                    constexpr int32_t TAG_NONE = INT32_MIN, TAG_STORE = INT32_MIN + 1;
-                    uint32_t val[EXEC_CHUNK_ROWS]; int32_t tag[EXEC_CHUNK_ROWS];
+                // tag: TAG_NONE = nothing to do, TAG_STORE = value loaded, otherwise the (batch-relative, >= floor) source
+                // position of a match byte that had to wait.
+                constexpr int32_t TAG_NONE = INT32_MIN, TAG_STORE = INT32_MIN + 1;
+                constexpr int R = (int)EXEC_CHUNK_ROWS;
+                auto load_chunk = [&](uint32_t r0, int32_t floor, uint32_t (&val)[R], int32_t (&tag)[R]) {
 #pragma unroll
-                    for (int i = 0; i < (int)EXEC_CHUNK_ROWS; i++) {
+                    for (int i = 0; i < R; i++) {
                         const uint32_t q = ((r0 + i) << 5) + lane;
                         const uint32_t word = lds32(a_mask + ((r0 + i) << 2));
                         const uint32_t owner = before + __popc(word & lt);   // sequences that ended below q
@@ -1157,26 +1168,28 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                             if (is_match && kk >= rc.y) sp = (int32_t)mst - (int32_t)rc.y + (int32_t)(kk % rc.y);
                         }
                         const bool valid = q < T;
-                        const bool dep = is_match && sp >= chunk0;
+                        const bool dep = is_match && sp >= floor;
                         const int32_t idx = is_match ? sp : (int32_t)(q - (rc.x >> 16));
                         const uint8_t *bp = is_match ? (const uint8_t *)bout : litq;
                         tag[i] = valid ? (dep ? sp : TAG_STORE) : TAG_NONE;
                         val[i] = 0;
                         if (valid && !dep) val[i] = bp[idx];
                     }
+                };
+                auto store_chunk = [&](uint32_t r0, int32_t floor, const uint32_t (&val)[R], const int32_t (&tag)[R]) {
 #pragma unroll
-                    for (int i = 0; i < (int)EXEC_CHUNK_ROWS; i++)
+                    for (int i = 0; i < R; i++)
                         if (tag[i] == TAG_STORE) bout[((r0 + i) << 5) + lane] = (uint8_t)val[i];
-                    // dependent bytes (source inside this chunk), rows in order
+                    // dependent bytes, rows in order (sources in earlier rows are final, inside the row the lowest pending byte is ready)
                     bool anydep = false;
 #pragma unroll
-                    for (int i = 0; i < (int)EXEC_CHUNK_ROWS; i++) anydep |= tag[i] >= chunk0;
+                    for (int i = 0; i < R; i++) anydep |= tag[i] >= floor;
                     if (__any_sync(0xffffffffu, anydep)) {
 #pragma unroll
-                        for (int i = 0; i < (int)EXEC_CHUNK_ROWS; i++) {
-                            bool mine = tag[i] >= chunk0;
+                        for (int i = 0; i < R; i++) {
+                            bool mine = tag[i] >= floor;
                             uint32_t pending = __ballot_sync(0xffffffffu, mine);
-                            const int32_t row0 = chunk0 + (i << 5);
+                            const int32_t row0 = (int32_t)((r0 + i) << 5);
                             while (pending) {
                                 __syncwarp();
                                 bool ready = mine && (tag[i] < row0 || !((pending >> (tag[i] - row0)) & 1u));
@@ -1186,7 +1199,29 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                         }
                     }
                     __syncwarp();
+                };
+#if B200Z_EXEC_PIPE
+                {
+                    uint32_t va[R]; int32_t ta[R];
+                    load_chunk(0, 0, va, ta);
+                    for (uint32_t r0 = 0; r0 < nrows; r0 += R) {
+                        uint32_t vb[R]; int32_t tb[R];
+                        const int32_t floor_a = r0 ? (int32_t)((r0 - R) << 5) : 0;
+#pragma unroll
+                        for (int i = 0; i < R; i++) { vb[i] = 0; tb[i] = TAG_NONE; }
+                        if (r0 + R < nrows) load_chunk(r0 + R, (int32_t)(r0 << 5), vb, tb);
+                        store_chunk(r0, floor_a, va, ta);
+#pragma unroll
+                        for (int i = 0; i < R; i++) { va[i] = vb[i]; ta[i] = tb[i]; }
+                    }
                 }
+#else
+                for (uint32_t r0 = 0; r0 < nrows; r0 += R) {
+                    uint32_t va[R]; int32_t ta[R];
+                    load_chunk(r0, (int32_t)(r0 << 5), va, ta);
+                    store_chunk(r0, (int32_t)(r0 << 5), va, ta);
+                }
+#endif
                 __syncwarp();
                 st.produced += T; st.counter += T; st.litpos += L;
             }
