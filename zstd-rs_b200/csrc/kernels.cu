@@ -262,6 +262,18 @@ struct RingBits {
     }
 };
 
+// ---- shared-memory accessors by 32-bit shared address
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
+__device__ __forceinline__ void red_or_shared(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+
 // Position-based reversed bit reader for k_fse's fast path.  The only state is P = bits_remaining()
 // (bit_reader_reverse.rs:27-29); every read assembles the 64 bits below position P from three words of a per-lane
 // shared-memory ring (8 groups of 16 bytes + a mirror of the top group below slot 0, so that the three words are
@@ -399,36 +411,44 @@ struct HufBits {
 // literals_section_decoder.rs:112-121).  Returns true when regular; otherwise the caller replays with huf_stream2.
 __device__ __forceinline__ bool huf_stream_fast(const uint8_t *__restrict__ tsym, const uint8_t *__restrict__ tnb, uint32_t mb,
                                                 const uint8_t *src, uint32_t len, uint8_t *dst, uint32_t cap, uint32_t ring_addr) {
-    RingBits br;
-    if (!br.init(src, len, ring_addr)) return false;
+    PosRing br;
+    if (!br.init(src, len, ring_addr + 16u)) return false;   // slot 0 of the ring; the mirror slot sits below it
     const uint32_t sh = 32u - mb;
-    uint32_t n = 0;
-    auto sym1 = [&]() -> uint32_t {
-        uint32_t idx = br.hi >> sh;
-        uint32_t s = tsym[idx];
-        br.skip((tnb[idx >> 1] >> ((idx & 1u) * 4u)) & 15u);
+    uint32_t a_sym = (uint32_t)__cvta_generic_to_shared(tsym), a_nb = (uint32_t)__cvta_generic_to_shared(tnb);
+    asm volatile("" : "+r"(a_sym), "+r"(a_nb));
+    // one symbol out of the window hi:lo (left aligned): LUT index = the top max_bits bits (huff0_decoder.rs:25-53)
+    auto sym1 = [&](uint32_t &hi, uint32_t &lo, uint32_t &used) -> uint32_t {
+        const uint32_t idx = hi >> sh;
+        const uint32_t s = lds8(a_sym + idx);
+        const uint32_t nb = (lds8(a_nb + (idx >> 1)) >> ((idx & 1u) * 4u)) & 15u;
+        hi = __funnelshift_l(lo, hi, nb);
+        lo <<= nb;
+        used += nb;
         return s;
     };
+    auto one = [&]() -> uint32_t { uint32_t hi, lo, used = 0; br.window(hi, lo); const uint32_t s = sym1(hi, lo, used); br.P -= (int32_t)used; br.service(); return s; };
+    uint32_t n = 0;
     // scalar head until dst + n is 16-byte aligned
     uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
     if (head > cap) head = cap;
-    for (; n < head; n++) { br.refill(); dst[n] = (uint8_t)sym1(); br.service(); }
+    for (; n < head; n++) dst[n] = (uint8_t)one();
+    // 16 symbols per store; a window of 64 bits feeds four symbols (<= 44 bits)
     for (; n + 16 <= cap; n += 16) {
         uint32_t w[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            br.refill();
-            uint32_t s0 = sym1(), s1 = sym1();
-            br.refill();
-            uint32_t s2 = sym1(), s3 = sym1();
-            br.service();
+            uint32_t hi, lo, used = 0;
+            br.window(hi, lo);
+            const uint32_t s0 = sym1(hi, lo, used), s1 = sym1(hi, lo, used), s2 = sym1(hi, lo, used), s3 = sym1(hi, lo, used);
+            br.P -= (int32_t)used;
+            if (q & 1) br.service();                  // every 8 symbols (<= 88 bits)
             w[q] = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
         }
         *reinterpret_cast<uint4 *>(dst + n) = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    for (; n < cap; n++) { br.refill(); dst[n] = (uint8_t)sym1(); br.service(); }
+    for (; n < cap; n++) dst[n] = (uint8_t)one();
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    return br.p == 0;
+    return br.P == 0;
 }
 
 // returns 0 exhausted exactly, 1 over-read, 2 cap reached, 3 ExtraPadding
@@ -890,10 +910,13 @@ struct LitSrc { const uint8_t *p; uint32_t rle; uint8_t byte; uint32_t regen; };
 
 // exact sequential execution of up to 32 sequences held one per lane (my_ll/my_ml/my_of); `resolved` = offsets
 // already went through do_offset_history.  Returns 0 or an error code.
-__device__ uint32_t exec_batch_exact(ExecState &st, const LitSrc &lit, const FrameDesc &fd, uint8_t *out, uint32_t nb, uint32_t my_ll, uint32_t my_ml,
-                                     uint32_t my_of, bool resolved, uint32_t lane) {
+// Sequence j of the batch lives in lane j >> 1, slot j & 1 (two records per lane: a = even, b = odd).
+__device__ uint32_t exec_batch_exact(ExecState &st, const LitSrc &lit, const FrameDesc &fd, uint8_t *out, uint32_t nb, uint32_t ll_a, uint32_t ml_a,
+                                     uint32_t of_a, uint32_t ll_b, uint32_t ml_b, uint32_t of_b, bool resolved, uint32_t lane) {
     for (uint32_t j = 0; j < nb; j++) {
-        uint32_t ll = __shfl_sync(0xffffffffu, my_ll, j), ml = __shfl_sync(0xffffffffu, my_ml, j), of = __shfl_sync(0xffffffffu, my_of, j);
+        const bool odd = (j & 1u) != 0;
+        uint32_t ll = __shfl_sync(0xffffffffu, odd ? ll_b : ll_a, j >> 1), ml = __shfl_sync(0xffffffffu, odd ? ml_b : ml_a, j >> 1),
+                 of = __shfl_sync(0xffffffffu, odd ? of_b : of_a, j >> 1);
         if (ll > 0) {
             if ((uint64_t)st.litpos + ll > lit.regen) return B200Z_ERR_EXEC_NOT_ENOUGH_BYTES_FOR_SEQUENCE;
             if (st.produced + ll > st.cap) return B200Z_ERR_TARGET_TOO_SMALL;
@@ -941,6 +964,11 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ uint2 ld_cg_u32x2(const uint32_t *p) {
+    uint2 v;
+    asm volatile("ld.global.cg.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) {
     uint32_t v;
@@ -963,16 +991,8 @@ __device__ __forceinline__ uint32_t exec_wait_progress(const BlockAux *aux, uint
     return __shfl_sync(0xffffffffu, v, 0);
 }
 
-__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ uint4 lds128(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
-__device__ __forceinline__ void red_or_shared(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-
 constexpr uint32_t EXEC_WARPS = 4;
+constexpr uint32_t EXEC_BATCH = 64;                         // sequences per batch: two per lane
 constexpr uint32_t EXEC_TMAX = 8128;                        // most bytes one batch of 32 sequences may produce on the fast path
 #ifndef B200Z_EXEC_CHUNK_ROWS
 #define B200Z_EXEC_CHUNK_ROWS 4
@@ -995,7 +1015,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                                                         const uint32_t *__restrict__ seq_scratch, uint8_t *__restrict__ output, uint64_t output_cap,
                                                         uint32_t nframes) {
     __shared__ uint32_t s_mask[EXEC_WARPS][EXEC_MASK_WORDS];
-    __shared__ uint2 s_recs[EXEC_WARPS][32];
+    __shared__ __align__(16) uint2 s_recs[EXEC_WARPS][EXEC_BATCH];
     const uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31, lt = lanemask_lt();
     if (f >= nframes) return;
@@ -1052,92 +1072,91 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
             const bool resolved = resolved_u != 0;
             __syncwarp();
             // sequence records stream in from k_fse, which may still be decoding this block: `avail` = published count.
-            // Records are prefetched one batch ahead when they are already there.
+            // A batch is 64 sequences, two per lane (2 * lane and 2 * lane + 1: 24 contiguous bytes); the next batch's
+            // records are requested into L2 one batch ahead.
             uint32_t avail = 0;
-            uint32_t nx_ll = 0, nx_ml = 0, nx_of = 1;
-            bool nx_loaded = false;
-            for (uint32_t base = 0; base < nseq_u && !e; base += 32) {
-                const uint32_t nb = nseq_u - base < 32 ? nseq_u - base : 32;
+            for (uint32_t base = 0; base < nseq_u && !e; base += EXEC_BATCH) {
+                const uint32_t nb = nseq_u - base < EXEC_BATCH ? nseq_u - base : EXEC_BATCH;
                 if (avail < base + nb) {
                     avail = exec_wait_progress(aux, b, base + nb, lane);
                     if (avail == 0xFFFFFFFEu) { e = B200Z_ERR_CUDA; break; }
                 }
-                uint32_t my_ll = nx_ll, my_ml = nx_ml, my_of = nx_of;
-                if (!nx_loaded) {
-                    my_ll = 0; my_ml = 0; my_of = 1;
-                    if (lane < nb) { const uint32_t *s = seqs + (uint64_t)(base + lane) * 3; my_ll = ld_cg_u32(s); my_ml = ld_cg_u32(s + 1); my_of = ld_cg_u32(s + 2); }
+                uint32_t ll_a = 0, ml_a = 0, of_a = 1, ll_b = 0, ml_b = 0, of_b = 1;
+                const bool on_a = 2u * lane < nb, on_b = 2u * lane + 1u < nb;
+                {
+                    const uint32_t *sp = seqs + (uint64_t)(base + 2u * lane) * 3;
+                    if (on_b) {
+                        const uint2 r0 = ld_cg_u32x2(sp), r1 = ld_cg_u32x2(sp + 2), r2 = ld_cg_u32x2(sp + 4);
+                        ll_a = r0.x; ml_a = r0.y; of_a = r1.x; ll_b = r1.y; ml_b = r2.x; of_b = r2.y;
+                    } else if (on_a) { ll_a = ld_cg_u32(sp); ml_a = ld_cg_u32(sp + 1); of_a = ld_cg_u32(sp + 2); }
+                    if (base + EXEC_BATCH < nseq_u && lane * 128u < (nseq_u - base - EXEC_BATCH) * 12u && lane < 6u) prefetch_l2(reinterpret_cast<const uint8_t *>(seqs + (uint64_t)(base + EXEC_BATCH) * 3) + lane * 128u);
                 }
-                nx_ll = 0; nx_ml = 0; nx_of = 1; nx_loaded = false;
-                if (base + 32 < nseq_u) {
-                    const uint32_t nb2 = nseq_u - base - 32 < 32 ? nseq_u - base - 32 : 32;
-                    if (avail < base + 32 + nb2) avail = ld_acquire_u32(&aux[b].progress);   // one look, no waiting
-                    if (avail >= base + 32 + nb2) {
-                        nx_loaded = true;
-                        if (lane < nb2) { const uint32_t *s = seqs + (uint64_t)(base + 32 + lane) * 3; nx_ll = ld_cg_u32(s); nx_ml = ld_cg_u32(s + 1); nx_of = ld_cg_u32(s + 2); }
-                    }
-                }
-                // inclusive scans of ll and ll + ml
-                uint32_t lit_end = my_ll, out_end = my_ll + my_ml;
+                // inclusive scans of ll and ll + ml over the lane pairs
+                uint32_t lit_end = ll_a + ll_b, out_end = ll_a + ml_a + ll_b + ml_b;
 #pragma unroll
                 for (int dd = 1; dd < 32; dd <<= 1) {
                     uint32_t a = __shfl_up_sync(0xffffffffu, lit_end, dd), c = __shfl_up_sync(0xffffffffu, out_end, dd);
                     if ((int)lane >= dd) { lit_end += a; out_end += c; }
                 }
                 const uint32_t T = __shfl_sync(0xffffffffu, out_end, 31), L = __shfl_sync(0xffffffffu, lit_end, 31);
+                const uint32_t out_end_b = out_end, out_end_a = out_end - ll_b - ml_b;      // inclusive ends of my two sequences
+                const uint32_t m_start_a = out_end_a - ml_a, m_start_b = out_end_b - ml_b;  // batch-relative starts of my matches
                 // offsets for the fast path must be resolved: blocks whose history is not a plan-time constant resolve here
-                uint32_t my_off = my_of;
-                bool fast = true;
+                uint32_t off_a = of_a, off_b = of_b;
+                uint32_t h0 = st.h0, h1 = st.h1, h2 = st.h2;
                 if (!resolved) {
-                    // 32 cheap scalar steps (sequence_execution.rs:59-118); keeps st.h* exact for the next batch
-                    uint32_t h0 = st.h0, h1 = st.h1, h2 = st.h2;
+                    // cheap scalar steps (sequence_execution.rs:59-118); committed only if the fast path is taken (the exact path
+                    // redoes the steps itself)
                     for (uint32_t j = 0; j < nb; j++) {
-                        uint32_t ll = __shfl_sync(0xffffffffu, my_ll, j), of = __shfl_sync(0xffffffffu, my_of, j);
+                        const bool odd = (j & 1u) != 0;
+                        uint32_t ll = __shfl_sync(0xffffffffu, odd ? ll_b : ll_a, j >> 1), of = __shfl_sync(0xffffffffu, odd ? of_b : of_a, j >> 1);
                         uint32_t actual = offset_history_step(of, ll, h0, h1, h2);
-                        if (lane == j) my_off = actual;
+                        if (lane == (j >> 1)) { if (odd) off_b = actual; else off_a = actual; }
                     }
-                    // committed only if the fast path is taken (the exact path redoes the steps itself)
-                    uint32_t m_start = out_end - my_ml;
-                    bool ok = lane >= nb || (my_off != 0 &&
-                                             (uint64_t)my_off <= st.produced - st.drained + m_start);
-                    fast = __all_sync(0xffffffffu, ok) && T <= EXEC_TMAX && (uint64_t)st.litpos + L <= lit.regen && st.produced + T <= st.cap && !lit.rle;
-                    if (fast) { st.h0 = h0; st.h1 = h1; st.h2 = h2; }
-                } else {
-                    uint32_t m_start = out_end - my_ml;
-                    bool ok = lane >= nb || (my_off != 0 &&
-                                             (uint64_t)my_off <= st.produced - st.drained + m_start);
-                    fast = __all_sync(0xffffffffu, ok) && T <= EXEC_TMAX && (uint64_t)st.litpos + L <= lit.regen && st.produced + T <= st.cap && !lit.rle;
                 }
+                const uint64_t reach = st.produced - st.drained;   // bytes of earlier output a match may reach back into
+                const bool ok = (!on_a || (off_a != 0 && (uint64_t)off_a <= reach + m_start_a)) && (!on_b || (off_b != 0 && (uint64_t)off_b <= reach + m_start_b));
+                const bool fast = __all_sync(0xffffffffu, ok) && T <= EXEC_TMAX && (uint64_t)st.litpos + L <= lit.regen && st.produced + T <= st.cap && !lit.rle;
                 if (!fast) {
-                    e = exec_batch_exact(st, lit, fd, out, nb, my_ll, my_ml, my_of, resolved, lane);
+                    e = exec_batch_exact(st, lit, fd, out, nb, ll_a, ml_a, of_a, ll_b, ml_b, of_b, resolved, lane);
                     continue;
                 }
+                if (!resolved) { st.h0 = h0; st.h1 = h1; st.h2 = h2; }
                 // ---------------- fast path
                 // Sequence j owns the bytes [lit_begin_j, out_end_j): its literal run, then its match.  A bit is set at
                 // the last byte of every sequence, so the owner of output byte q is the number of set bits below q;
-                // one 16-byte shared-memory record per sequence then tells the byte where it comes from.
-                const uint32_t m_start = out_end - my_ml;              // batch-relative start of my match
-                const uint32_t m_before = m_start - lit_end;           // match bytes of the earlier sequences of the batch
+                // one 8-byte shared-memory record per sequence then tells the byte where it comes from.
+                const uint32_t lit_end_a = lit_end - ll_b;
+                const uint32_t m_before_a = m_start_a - lit_end_a, m_before_b = m_start_b - lit_end;   // match bytes of the earlier sequences
                 const uint32_t nrows = (T + 31) >> 5;
                 // The batch's match sources are scattered over the frame's window, and with thousands of frames in flight the
                 // windows do not stay in L2: ask for the sectors now, a few hundred instructions before the rows need them.
-                if (!B200Z_EXEC_PREFETCH) {
-                } else if (lane < nb) {
-                    const uint8_t *src = out + st.produced + m_start - my_off;
-                    prefetch_l2(src);
-                    if ((((uint32_t)(uintptr_t)src) & 31u) + my_ml > 32u) prefetch_l2(src + my_ml - 1);
-                } else if (lane == 31) {
-                    const uint32_t ahead = st.litpos + L + 256u;   // the literal stream is sequential: stay two lines ahead
-                    prefetch_l2(lit.p + (ahead < lit.regen ? ahead : lit.regen - 1));
+                if (B200Z_EXEC_PREFETCH) {
+                    if (on_a) {
+                        const uint8_t *src = out + st.produced + m_start_a - off_a;
+                        prefetch_l2(src);
+                        if ((((uint32_t)(uintptr_t)src) & 31u) + ml_a > 32u) prefetch_l2(src + ml_a - 1);
+                    }
+                    if (on_b) {
+                        const uint8_t *src = out + st.produced + m_start_b - off_b;
+                        prefetch_l2(src);
+                        if ((((uint32_t)(uintptr_t)src) & 31u) + ml_b > 32u) prefetch_l2(src + ml_b - 1);
+                    }
+                    if (lane == 31) {
+                        const uint32_t ahead = st.litpos + L + 256u;   // the literal stream is sequential: stay two lines ahead
+                        prefetch_l2(lit.p + (ahead < lit.regen ? ahead : lit.regen - 1));
+                    }
                 }
                 sts32(a_mask + (lane << 2), 0u);
                 if (nrows > 32u - EXEC_CHUNK_ROWS)
                     for (uint32_t w = lane + 32; w < ((nrows + EXEC_CHUNK_ROWS - 1u) & ~(EXEC_CHUNK_ROWS - 1u)); w += 32) sts32(a_mask + (w << 2), 0u);
                 // 8-byte record: literal byte q of the sequence is literal number (q - m_before) of the batch, match byte q
-                // comes from output position q - offset (m_start <= 32 * 254, m_before <= 32 * 127: 16 bits each)
-                sts64(a_recs + (lane << 3), m_start | (m_before << 16), my_off);
-                const bool has_ovl = __any_sync(0xffffffffu, my_off < my_ml);   // some match overlaps its own output (rare)
+                // comes from output position q - offset (m_start, m_before <= EXEC_TMAX: 16 bits each)
+                sts128(a_recs + (lane << 4), m_start_a | (m_before_a << 16), off_a, m_start_b | (m_before_b << 16), off_b);
+                const bool has_ovl = __any_sync(0xffffffffu, off_a < ml_a || off_b < ml_b);   // some match overlaps its own output (rare)
                 __syncwarp();
-                if (lane < nb) red_or_shared(a_mask + (((out_end - 1) >> 5) << 2), 1u << ((out_end - 1) & 31u));
+                if (on_a) red_or_shared(a_mask + (((out_end_a - 1) >> 5) << 2), 1u << ((out_end_a - 1) & 31u));
+                if (on_b) red_or_shared(a_mask + (((out_end_b - 1) >> 5) << 2), 1u << ((out_end_b - 1) & 31u));
                 __syncwarp();
                 uint8_t *bout = out + st.produced;
                 const uint8_t *litq = lit.p + st.litpos;
@@ -1159,7 +1178,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                         const uint32_t word = lds32(a_mask + ((r0 + i) << 2));
                         const uint32_t owner = before + __popc(word & lt);   // sequences that ended below q
                         before += __popc(word);
-                        const uint2 rc = lds64(a_recs + ((owner & 31u) << 3));
+                        const uint2 rc = lds64(a_recs + ((owner & (EXEC_BATCH - 1u)) << 3));
                         const uint32_t mst = rc.x & 0xffffu;
                         const bool is_match = q >= mst;
                         int32_t sp = (int32_t)q - (int32_t)rc.y;                  // batch-relative source of a match byte
