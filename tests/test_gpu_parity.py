@@ -492,3 +492,39 @@ def test_bitflip_sweep_matches_oracle(pkg, ctx, oracle):
         else:
             assert (bz[int(res[i]["status"])].replace("B200Z_", ""), int(res[i]["stage"])) == err, (i, res[i], err)
     assert same > 0
+
+
+def test_exec_run_shapes(pkg, ctx, oracle):
+    """Sequence shapes that steer k_exec's batch paths: overlapping matches (offset < length, incl. offset 1), matches and literal
+    runs far longer than a row, batches above the fast path's byte cap, odd sequence counts, repeat offsets after zero literal
+    lengths.  Bit-exact against the plaintext and the oracle."""
+    import datagen as G
+    rng = np.random.Generator(np.random.PCG64(0xE8EC))
+    def rnd(n): return rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+    text = G.gen_text(200000, 77).tobytes()
+    pieces = [
+        b"a" * 70000,                                                    # offset 1, length >> row: one long overlapping match
+        (b"abc" * 9000) + rnd(100) + (b"xy" * 20000),                    # short periods
+        rnd(3000) + b"\0" * 5000 + rnd(40) + b"\0" * 17 + rnd(9000),      # long literal runs around long matches
+        b"".join(text[i * 97:i * 97 + 61] + b"=" * (i % 40) for i in range(1500)),   # text with runs of every length 0..39
+        b"".join(rnd(700) + text[1000:1000 + 300 + i] for i in range(60)),           # ~1 KB per sequence: batches above the byte cap
+        text[:131072],
+        text[5000:5000 + 64 * 13 + 7],                                   # tiny frame, odd sequence count
+        b"".join(text[200 * i:200 * i + 40] * 3 for i in range(400)),    # immediate repeats: repeat offsets with zero literal length
+    ]
+    frames = [G.compress(np.frombuffer(p, dtype=np.uint8)) for p in pieces]
+    comp = np.frombuffer(b"".join(bytes(f) for f in frames), dtype=np.uint8)
+    io = np.zeros(len(frames), dtype=pkg.binding.FRAME_IO_DTYPE)
+    so = oo = 0
+    for i, (f, p) in enumerate(zip(frames, pieces)):
+        io[i] = (so, len(f), oo, len(p))
+        so += len(f); oo += len(p)
+    out = np.zeros(oo + 16, dtype=np.uint8)
+    res = pkg.decode_frames(ctx, comp, io, out)
+    assert (res["status"] == 0).all(), res[res["status"] != 0][:3]
+    plain = b"".join(pieces)
+    for i, p in enumerate(pieces):
+        got = out[io[i]["out_off"]:io[i]["out_off"] + len(p)].tobytes()
+        assert got == p, f"piece {i}: GPU output differs from the plaintext"
+        assert oracle.decode_frame(bytes(frames[i]))[0] == p
+    assert (out[oo:] == 0).all()

@@ -991,9 +991,15 @@ __device__ __forceinline__ uint32_t exec_wait_progress(const BlockAux *aux, uint
     return __shfl_sync(0xffffffffu, v, 0);
 }
 
-constexpr uint32_t EXEC_WARPS = 4;
+#ifndef B200Z_EXEC_WARPS
+#define B200Z_EXEC_WARPS 4
+#endif
+constexpr uint32_t EXEC_WARPS = B200Z_EXEC_WARPS;
 constexpr uint32_t EXEC_BATCH = 64;                         // sequences per batch: two per lane
-constexpr uint32_t EXEC_TMAX = 8128;                        // most bytes one batch of 32 sequences may produce on the fast path
+#ifndef B200Z_EXEC_TMAX
+#define B200Z_EXEC_TMAX 8128
+#endif
+constexpr uint32_t EXEC_TMAX = B200Z_EXEC_TMAX;             // most bytes one batch may produce on the fast path (sizes the end-bit mask)
 #ifndef B200Z_EXEC_CHUNK_ROWS
 #define B200Z_EXEC_CHUNK_ROWS 4
 #endif
