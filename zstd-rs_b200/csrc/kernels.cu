@@ -597,7 +597,15 @@ __global__ void __launch_bounds__(32) k_huf(const BlockDesc *__restrict__ descs,
 // reversed bitstream is read through a 64-bit window with the next aligned word prefetched, and sequences are
 // written four at a time as three 16-byte vectors.
 // ------------------------------------------------------------------------------------------------------------
-constexpr uint32_t FSE_BLOCKS_PER_CTA = 32;
+#ifndef B200Z_FSE_CHAINS
+#define B200Z_FSE_CHAINS 1
+#endif
+constexpr uint32_t FSE_CHAINS = B200Z_FSE_CHAINS;            // blocks per lane, decoded interleaved
+#ifndef B200Z_FSE_LANES
+#define B200Z_FSE_LANES 16
+#endif
+constexpr uint32_t FSE_LANES = B200Z_FSE_LANES;              // lanes of the warp that carry blocks
+constexpr uint32_t FSE_BLOCKS_PER_CTA = FSE_LANES * FSE_CHAINS;
 constexpr uint32_t FSE_TAB_U16 = 512 + 512 + 256;   // LL, ML, OF entries per block
 
 __constant__ uint32_t c_ll_base[36] = {0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,18,20,22,24,28,32,40,48,64,128,256,512,1024,2048,4096,8192,16384,32768,65536};
@@ -640,174 +648,86 @@ struct FseState {
     }
 };
 
-__global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs, BlockAux *__restrict__ aux, const uint8_t *__restrict__ input,
-                                          uint32_t *__restrict__ seq_scratch, uint32_t nblocks) {
-    extern __shared__ __align__(16) uint8_t smem_fse[];
-    uint16_t *tabs = reinterpret_cast<uint16_t *>(smem_fse);
-    uint32_t *s_ll_base = reinterpret_cast<uint32_t *>(smem_fse + FSE_BLOCKS_PER_CTA * FSE_TAB_U16 * 2);
-    uint32_t *s_ml_base = s_ll_base + 36;
-    uint8_t *s_ll_bits = reinterpret_cast<uint8_t *>(s_ml_base + 53);
-    uint8_t *s_ml_bits = s_ll_bits + 36;
-    uint32_t *s_ll = reinterpret_cast<uint32_t *>(smem_fse + FSE_BLOCKS_PER_CTA * FSE_TAB_U16 * 2 + 512);   // base | bits << 24
-    uint32_t *s_ml = s_ll + 36;
-    uint8_t *s_ring = smem_fse + FSE_BLOCKS_PER_CTA * FSE_TAB_U16 * 2 + 1024;                                // 32 x RING_STRIDE
-    const uint32_t lane = threadIdx.x;
-    const uint32_t b = blockIdx.x * FSE_BLOCKS_PER_CTA + lane;
-    for (uint32_t i = lane; i < 36; i += 32) { s_ll_base[i] = c_ll_base[i]; s_ll_bits[i] = c_ll_bits[i]; s_ll[i] = c_ll_base[i] | ((uint32_t)c_ll_bits[i] << 24); }
-    for (uint32_t i = lane; i < 53; i += 32) { s_ml_base[i] = c_ml_base[i]; s_ml_bits[i] = c_ml_bits[i]; s_ml[i] = c_ml_base[i] | ((uint32_t)c_ml_bits[i] << 24); }
+// One block's sequence decode on the fast path: everything a chain carries between steps.  A lane runs FSE_CHAINS of
+// them interleaved -- the chains are independent, so the second one's instructions fill the dependency stalls of the
+// first (one warp per scheduler: there is nobody else to issue).
+struct FseChain {
+    // per block
+    uint32_t b; const BlockDesc *d; bool active, run, bad; uint32_t st_seq;
+    const FseTab *tl, *to, *tm;
+    uint32_t logL, logM, logO, qTL, qTM, qTO;   // accuracy logs; shared-memory table addresses biased by -2^log entries
+    uint32_t *out; uint32_t nseq; bool resolve;
+    // running
+    PosRing br;
+    uint32_t eL, eM, eO, h0, h1, h2;
+    uint64_t sum_ml;
+    uint32_t flags, or_of, max_x, i;
+};
 
-    const bool active = b < nblocks;
-    const BlockDesc *d = active ? &descs[b] : nullptr;
-    uint32_t st_seq = 0;
-    bool run = false;
-    if (active) {
-        st_seq = aux[b].pad;
-        if (d->btype != BT_COMPRESSED) aux[b].out_size = d->raw_size;
-        else if (!d->host_status && d->nseq == 0) aux[b].out_size = d->regen_size;
-        run = d->btype == BT_COMPRESSED && !d->host_status && d->nseq != 0 && st_seq == 0;
-    }
-    const FseTab *tl = run ? d->ll : nullptr, *to = run ? d->of : nullptr, *tm = run ? d->ml : nullptr;
-    // ---- stage the tables of the 32 blocks (warp-cooperative, 16-byte vectors)
-    for (uint32_t j = 0; j < FSE_BLOCKS_PER_CTA; j++) {
-        const FseTab *pj[3];
-        pj[0] = (const FseTab *)(uintptr_t)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)tl, j);
-        pj[1] = (const FseTab *)(uintptr_t)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)tm, j);
-        pj[2] = (const FseTab *)(uintptr_t)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)to, j);
-        uint16_t *dstj = tabs + j * FSE_TAB_U16;
-        const uint32_t offs[3] = {0, 512, 1024};
-#pragma unroll
-        for (int t = 0; t < 3; t++) {
-            if (!pj[t] || !pj[t]->valid) continue;
-            uint32_t n16 = ((2u << pj[t]->log) + 15) >> 4;   // bytes / 16
-            if (t == 2 && n16 > 32) n16 = 32;
-            if (n16 > 64) n16 = 64;
-            const uint4 *s4 = reinterpret_cast<const uint4 *>(pj[t]->e);
-            uint4 *d4 = reinterpret_cast<uint4 *>(dstj + offs[t]);
-            for (uint32_t i = lane; i < n16; i += 32) d4[i] = s4[i];
-        }
-    }
-    __syncwarp();
-    if (!active) return;
-    if (!run) { aux[b].pad = st_seq; fse_publish(aux, b, FSE_PROGRESS_FINAL); return; }
+__device__ __forceinline__ uint32_t fse_lds16(uint32_t addr) { uint16_t w; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(w) : "r"(addr) : "memory"); return w; }
 
-    // ---------------- fast path: branch-free steps; anything unusual (bad code, > 32 extra bits in one sequence,
-    // under/over-run, uninitialised table) sets `bad` and the block is decoded again by the exact path below.
-    {
-        const uint8_t *src = input + d->src_off + aux[b].seq_bits_off;
-        const uint32_t len = d->src_size - aux[b].seq_bits_off;
-        const uint16_t *TL = tabs + lane * FSE_TAB_U16, *TM = TL + 512, *TO = TL + 1024;
-        PosRing br;
-        const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(s_ring + lane * RING_STRIDE) + 16u;   // slot 0; the mirror slot sits below
-        bool bad = !br.init(src, len, ring_addr) || !tl || !tl->valid || !to || !to->valid || !tm || !tm->valid;
-        if (!bad) {
-            const uint32_t logL = tl->log, logM = tm->log, logO = to->log;
-            // table byte addresses in shared memory, biased by -2^log entries: the next state is (f << nb) + bits - 2^log
-            const uint32_t aTL = (uint32_t)__cvta_generic_to_shared(TL), aTM = (uint32_t)__cvta_generic_to_shared(TM), aTO = (uint32_t)__cvta_generic_to_shared(TO);
-            const uint32_t pTL = aTL - (2u << logL), pTM = aTM - (2u << logM), pTO = aTO - (2u << logO);
-            const uint32_t aLL = (uint32_t)__cvta_generic_to_shared(s_ll), aML = (uint32_t)__cvta_generic_to_shared(s_ml);
-            auto lds16 = [](uint32_t addr) -> uint32_t { uint16_t w; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(w) : "r"(addr) : "memory"); return w; };
-            uint32_t eL, eM, eO;
-            {   // initial states LL, OF, ML (sequence_section_decoder.rs:164-166)
-                uint32_t hi, lo;
-                br.window(hi, lo);
-                const uint32_t t1 = shl_c(hi, logL), t2 = shl_c(t1, logO);
-                eL = lds16(aTL + (shr_c(hi, 32u - logL) << 1));
-                eO = lds16(aTO + (shr_c(t1, 32u - logO) << 1));
-                eM = lds16(aTM + (shr_c(t2, 32u - logM) << 1));
-                br.P -= (int32_t)(logL + logO + logM);
-            }
-            uint32_t *out = seq_scratch + d->seq_buf_off * 3;
-            const uint32_t nseq = d->nseq;
-            const bool resolve = d->fse_resolves != 0;
-            uint32_t h0 = d->init_hist[0], h1 = d->init_hist[1], h2 = d->init_hist[2];
-            uint64_t sum_ml = 0;
-            uint32_t flags = 0, or_of = 0, max_x = 0;
-            uint32_t stage[12];
-            uint32_t qTL = pTL, qTM = pTM, qTO = pTO, qLL = aLL, qML = aML;
-            asm volatile("" : "+r"(qTL), "+r"(qTM), "+r"(qTO), "+r"(qLL), "+r"(qML));   // keep the five table addresses in registers
-            auto step = [&](uint32_t &o_ll, uint32_t &o_ml, uint32_t &o_of, bool update) {
-                uint32_t hi, lo;
-                br.window(hi, lo);
-                const uint32_t cL = eL >> 10, cM = eM >> 10, cO = eO >> 10;
-                const uint32_t vL = br.lds(qLL + (cL << 2)), vM = br.lds(qML + (cM << 2));   // base | extra_bits << 24
-                const uint32_t xL = vL >> 24, xM = vM >> 24, xO = cO;
-                or_of |= cO;          // offset code > 31 is checked per group (LL/ML codes are capped by table construction, scratch.rs:36-40)
-                // extra bits: OF, ML, LL (get_bits_triple, sequence_section_decoder.rs:185)
-                const uint32_t xsum = xO + xM + xL;
-                max_x = max(max_x, xsum);   // > 32 extra bits in one sequence: not for this path, checked per group
-                const uint32_t t1 = shl_c(hi, xO), t2 = shl_c(t1, xM);
-                const uint32_t obits = shr_c(hi, 32u - xO), ml_add = shr_c(t1, 32u - xM), ll_add = shr_c(t2, 32u - xL);
-                uint32_t offset = obits + (1u << (cO & 31u));
-                const uint32_t ll = (vL & 0xFFFFFFu) + ll_add, ml = (vM & 0xFFFFFFu) + ml_add;
-                sum_ml += ml;
-                {   // do_offset_history (sequence_execution.rs:59-118), branch-free; the result is used only when `resolve`
-                    const bool rep = offset <= 3u;
-                    const uint32_t r = offset - 1u + (ll == 0u ? 1u : 0u);   // 0..3 when rep
-                    const uint32_t h0m1 = h0 - (h0 != 0u ? 1u : 0u);          // saturating_sub (:74)
-                    uint32_t cand = h0;
-                    cand = r == 1u ? h1 : cand;
-                    cand = r == 2u ? h2 : cand;
-                    cand = r == 3u ? h0m1 : cand;
-                    const uint32_t actual = rep ? cand : offset - 3u;
-                    const bool keep2 = rep && r <= 1u, keep1 = rep && r == 0u;
-                    h2 = keep2 ? h2 : h1;
-                    h1 = keep1 ? h1 : h0;
-                    h0 = actual;
-                    offset = resolve ? actual : offset;
-                }
-                o_ll = ll; o_ml = ml; o_of = offset;
-                if (update) {   // state updates LL, ML, OF (:198-207); compact entries (b200z_types.h): nb = log - floor(log2 f)
-                    const uint32_t fL = eL & 1023u, fM = eM & 1023u, fO = eO & 1023u;
-                    const uint32_t nbL = logL - bfind32(fL), nbM = logM - bfind32(fM), nbO = logO - bfind32(fO);
-                    const uint32_t u0 = fsl_c(lo, hi, xsum);                 // the 32 bits below the extra bits
-                    const uint32_t u1 = shl_c(u0, nbL), u2 = shl_c(u1, nbM);
-                    const uint32_t aL = shr_c(u0, 32u - nbL), aM = shr_c(u1, 32u - nbM), aO = shr_c(u2, 32u - nbO);
-                    eL = lds16(qTL + (((fL << nbL) + aL) << 1));
-                    eM = lds16(qTM + (((fM << nbM) + aM) << 1));
-                    eO = lds16(qTO + (((fO << nbO) + aO) << 1));
-                    br.P -= (int32_t)(xsum + nbL + nbM + nbO);
-                } else br.P -= (int32_t)xsum;
-            };
-            uint32_t i = 0;
-            for (; i + 4 < nseq; i += 4) {
-#pragma unroll
-                for (int q = 0; q < 4; q++) { step(stage[3 * q], stage[3 * q + 1], stage[3 * q + 2], true); if (q & 1) br.service(); }
-                flags |= (uint32_t)(br.P < 0) | (uint32_t)(max_x > 32u) | (or_of >> 5);   // bits_remaining only decreases: one check per group is equivalent
-                uint4 *o4 = reinterpret_cast<uint4 *>(out + 3 * i);
-                o4[0] = make_uint4(stage[0], stage[1], stage[2], stage[3]);
-                o4[1] = make_uint4(stage[4], stage[5], stage[6], stage[7]);
-                o4[2] = make_uint4(stage[8], stage[9], stage[10], stage[11]);
-                if (flags) break;
-                if (((i + 4) & 127u) == 0) fse_publish(aux, b, i + 4);   // every 128 sequences: the fence costs ~1 us
-            }
-            if (!flags) {
-                for (; i < nseq; i++) {
-                    uint32_t ll, ml, of;
-                    step(ll, ml, of, i + 1 < nseq);
-                    br.service();
-                    flags |= (uint32_t)(br.P < 0) | (uint32_t)(max_x > 32u) | (or_of >> 5);
-                    out[3 * i] = ll; out[3 * i + 1] = ml; out[3 * i + 2] = of;
-                }
-            }
-            bad = flags != 0 || br.P != 0;
-            if (!bad) {
-                aux[b].pad = 0;
-                if (resolve) { aux[b].hist_after[0] = h0; aux[b].hist_after[1] = h1; aux[b].hist_after[2] = h2; }
-                uint64_t total = sum_ml + d->regen_size;
-                aux[b].out_size = (uint32_t)(total > 0xffffffffull ? 0xffffffffull : total);
-            }
-        }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (!bad) { fse_publish(aux, b, FSE_PROGRESS_FINAL); return; }
+// one sequence (sequence_section_decoder.rs:168-207); `update` = not the block's last sequence
+__device__ __forceinline__ void fse_step(FseChain &c, uint32_t qLL, uint32_t qML, uint32_t &o_ll, uint32_t &o_ml, uint32_t &o_of, bool update) {
+    uint32_t hi, lo;
+    c.br.window(hi, lo);
+    const uint32_t cL = c.eL >> 10, cM = c.eM >> 10, cO = c.eO >> 10;
+    const uint32_t vL = lds32(qLL + (cL << 2)), vM = lds32(qML + (cM << 2));   // base | extra_bits << 24
+    const uint32_t xL = vL >> 24, xM = vM >> 24, xO = cO;
+    c.or_of |= cO;          // offset code > 31 is checked per group (LL/ML codes are capped by table construction, scratch.rs:36-40)
+    // extra bits: OF, ML, LL (get_bits_triple, sequence_section_decoder.rs:185)
+    const uint32_t xsum = xO + xM + xL;
+    c.max_x = max(c.max_x, xsum);   // > 32 extra bits in one sequence: not for this path, checked per group
+    const uint32_t t1 = shl_c(hi, xO), t2 = shl_c(t1, xM);
+    const uint32_t obits = shr_c(hi, 32u - xO), ml_add = shr_c(t1, 32u - xM), ll_add = shr_c(t2, 32u - xL);
+    uint32_t offset = obits + (1u << (cO & 31u));
+    const uint32_t ll = (vL & 0xFFFFFFu) + ll_add, ml = (vM & 0xFFFFFFu) + ml_add;
+    c.sum_ml += ml;
+    {   // do_offset_history (sequence_execution.rs:59-118), branch-free; the result is used only when `resolve`
+        const bool rep = offset <= 3u;
+        const uint32_t r = offset - 1u + (ll == 0u ? 1u : 0u);   // 0..3 when rep
+        const uint32_t h0m1 = c.h0 - (c.h0 != 0u ? 1u : 0u);      // saturating_sub (:74)
+        uint32_t cand = c.h0;
+        cand = r == 1u ? c.h1 : cand;
+        cand = r == 2u ? c.h2 : cand;
+        cand = r == 3u ? h0m1 : cand;
+        const uint32_t actual = rep ? cand : offset - 3u;
+        const bool keep2 = rep && r <= 1u, keep1 = rep && r == 0u;
+        c.h2 = keep2 ? c.h2 : c.h1;
+        c.h1 = keep1 ? c.h1 : c.h0;
+        c.h0 = actual;
+        offset = c.resolve ? actual : offset;
     }
-    // ---------------- exact path (rare): the reference's control flow, one check at a time
+    o_ll = ll; o_ml = ml; o_of = offset;
+    if (update) {   // state updates LL, ML, OF (:198-207); compact entries (b200z_types.h): nb = log - floor(log2 f)
+        const uint32_t fL = c.eL & 1023u, fM = c.eM & 1023u, fO = c.eO & 1023u;
+        const uint32_t nbL = c.logL - bfind32(fL), nbM = c.logM - bfind32(fM), nbO = c.logO - bfind32(fO);
+        const uint32_t u0 = fsl_c(lo, hi, xsum);                 // the 32 bits below the extra bits
+        const uint32_t u1 = shl_c(u0, nbL), u2 = shl_c(u1, nbM);
+        const uint32_t aL = shr_c(u0, 32u - nbL), aM = shr_c(u1, 32u - nbM), aO = shr_c(u2, 32u - nbO);
+        c.eL = fse_lds16(c.qTL + (((fL << nbL) + aL) << 1));
+        c.eM = fse_lds16(c.qTM + (((fM << nbM) + aM) << 1));
+        c.eO = fse_lds16(c.qTO + (((fO << nbO) + aO) << 1));
+        c.br.P -= (int32_t)(xsum + nbL + nbM + nbO);
+    } else c.br.P -= (int32_t)xsum;
+}
+__device__ __forceinline__ void fse_group_end(FseChain &c, const uint32_t (&stage)[12]) {
+    c.flags |= (uint32_t)(c.br.P < 0) | (uint32_t)(c.max_x > 32u) | (c.or_of >> 5);   // bits_remaining only decreases: one check per group is equivalent
+    uint4 *o4 = reinterpret_cast<uint4 *>(c.out + 3 * c.i);
+    o4[0] = make_uint4(stage[0], stage[1], stage[2], stage[3]);
+    o4[1] = make_uint4(stage[4], stage[5], stage[6], stage[7]);
+    o4[2] = make_uint4(stage[8], stage[9], stage[10], stage[11]);
+}
+
+// the exact path (rare): the reference's control flow, one check at a time, for one block
+__device__ __noinline__ void fse_exact_block(const BlockDesc *d, BlockAux *aux, uint32_t b, const uint8_t *input, uint32_t *seq_scratch,
+                                             const uint16_t *TL, const uint16_t *TM, const uint16_t *TO, const FseTab *tl, const FseTab *to, const FseTab *tm,
+                                             const uint32_t *s_ll_base, const uint32_t *s_ml_base, const uint8_t *s_ll_bits, const uint8_t *s_ml_bits, uint32_t st_seq) {
     uint32_t err = 0;
     uint64_t sum_ml = 0, sum_ll = 0;
     uint32_t h0r = 0, h1r = 0, h2r = 0;
     {
         const uint8_t *src = input + d->src_off + aux[b].seq_bits_off;
         uint32_t len = d->src_size - aux[b].seq_bits_off;
-        const uint16_t *TL = tabs + lane * FSE_TAB_U16, *TM = TL + 512, *TO = TL + 1024;
         HufBits br;
         FseState sl{0}, so{0}, sm{0};
         uint32_t logL = 0, logM = 0, logO = 0;
@@ -875,6 +795,170 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
     uint64_t total = sum_ml + d->regen_size;
     aux[b].out_size = (uint32_t)(total > 0xffffffffull ? 0xffffffffull : total);
     fse_publish(aux, b, FSE_PROGRESS_FINAL);
+}
+
+__global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs, BlockAux *__restrict__ aux, const uint8_t *__restrict__ input,
+                                          uint32_t *__restrict__ seq_scratch, uint32_t nblocks) {
+    extern __shared__ __align__(16) uint8_t smem_fse[];
+    uint16_t *tabs = reinterpret_cast<uint16_t *>(smem_fse);
+    uint32_t *s_ll_base = reinterpret_cast<uint32_t *>(smem_fse + FSE_BLOCKS_PER_CTA * FSE_TAB_U16 * 2);
+    uint32_t *s_ml_base = s_ll_base + 36;
+    uint8_t *s_ll_bits = reinterpret_cast<uint8_t *>(s_ml_base + 53);
+    uint8_t *s_ml_bits = s_ll_bits + 36;
+    uint32_t *s_ll = reinterpret_cast<uint32_t *>(smem_fse + FSE_BLOCKS_PER_CTA * FSE_TAB_U16 * 2 + 512);   // base | bits << 24
+    uint32_t *s_ml = s_ll + 36;
+    uint8_t *s_ring = smem_fse + FSE_BLOCKS_PER_CTA * FSE_TAB_U16 * 2 + 1024;                                // FSE_BLOCKS_PER_CTA x RING_STRIDE
+    const uint32_t lane = threadIdx.x;
+    for (uint32_t i = lane; i < 36; i += 32) { s_ll_base[i] = c_ll_base[i]; s_ll_bits[i] = c_ll_bits[i]; s_ll[i] = c_ll_base[i] | ((uint32_t)c_ll_bits[i] << 24); }
+    for (uint32_t i = lane; i < 53; i += 32) { s_ml_base[i] = c_ml_base[i]; s_ml_bits[i] = c_ml_bits[i]; s_ml[i] = c_ml_base[i] | ((uint32_t)c_ml_bits[i] << 24); }
+
+    FseChain ch[FSE_CHAINS];
+#pragma unroll
+    for (int k = 0; k < (int)FSE_CHAINS; k++) {
+        FseChain &c = ch[k];
+        c.b = blockIdx.x * FSE_BLOCKS_PER_CTA + FSE_CHAINS * lane + k;   // neighbouring blocks share a lane: similar lengths
+        c.active = lane < FSE_LANES && c.b < nblocks;
+        c.d = c.active ? &descs[c.b] : nullptr;
+        c.st_seq = 0; c.run = false; c.bad = false;
+        if (c.active) {
+            c.st_seq = aux[c.b].pad;
+            if (c.d->btype != BT_COMPRESSED) aux[c.b].out_size = c.d->raw_size;
+            else if (!c.d->host_status && c.d->nseq == 0) aux[c.b].out_size = c.d->regen_size;
+            c.run = c.d->btype == BT_COMPRESSED && !c.d->host_status && c.d->nseq != 0 && c.st_seq == 0;
+        }
+        c.tl = c.run ? c.d->ll : nullptr; c.to = c.run ? c.d->of : nullptr; c.tm = c.run ? c.d->ml : nullptr;
+    }
+    // ---- stage the tables of the CTA's blocks (warp-cooperative, 16-byte vectors); slot = FSE_CHAINS * lane + chain
+    for (uint32_t j = 0; j < FSE_LANES; j++) {
+#pragma unroll
+        for (int k = 0; k < (int)FSE_CHAINS; k++) {
+            const FseTab *pj[3];
+            pj[0] = (const FseTab *)(uintptr_t)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)ch[k].tl, j);
+            pj[1] = (const FseTab *)(uintptr_t)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)ch[k].tm, j);
+            pj[2] = (const FseTab *)(uintptr_t)__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)ch[k].to, j);
+            uint16_t *dstj = tabs + (FSE_CHAINS * j + k) * FSE_TAB_U16;
+            const uint32_t offs[3] = {0, 512, 1024};
+#pragma unroll
+            for (int t = 0; t < 3; t++) {
+                if (!pj[t] || !pj[t]->valid) continue;
+                uint32_t n16 = ((2u << pj[t]->log) + 15) >> 4;   // bytes / 16
+                if (t == 2 && n16 > 32) n16 = 32;
+                if (n16 > 64) n16 = 64;
+                const uint4 *s4 = reinterpret_cast<const uint4 *>(pj[t]->e);
+                uint4 *d4 = reinterpret_cast<uint4 *>(dstj + offs[t]);
+                for (uint32_t i = lane; i < n16; i += 32) d4[i] = s4[i];
+            }
+        }
+    }
+    __syncwarp();
+    uint32_t qLL = (uint32_t)__cvta_generic_to_shared(s_ll), qML = (uint32_t)__cvta_generic_to_shared(s_ml);
+    asm volatile("" : "+r"(qLL), "+r"(qML));
+
+    // ---------------- fast path: branch-free steps; anything unusual (bad code, > 32 extra bits in one sequence,
+    // under/over-run, uninitialised table) sets `bad` and the block is decoded again by the exact path below.
+#pragma unroll
+    for (int k = 0; k < (int)FSE_CHAINS; k++) {
+        FseChain &c = ch[k];
+        if (!c.run) { c.bad = false; continue; }
+        const uint32_t slot = FSE_CHAINS * lane + k;
+        const uint8_t *src = input + c.d->src_off + aux[c.b].seq_bits_off;
+        const uint32_t len = c.d->src_size - aux[c.b].seq_bits_off;
+        const uint16_t *TL = tabs + slot * FSE_TAB_U16;
+        const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(s_ring + slot * RING_STRIDE) + 16u;   // slot 0; the mirror slot sits below
+        c.bad = !c.br.init(src, len, ring_addr) || !c.tl || !c.tl->valid || !c.to || !c.to->valid || !c.tm || !c.tm->valid;
+        c.flags = 0; c.or_of = 0; c.max_x = 0; c.i = 0; c.sum_ml = 0;
+        c.nseq = c.d->nseq; c.resolve = c.d->fse_resolves != 0;
+        c.h0 = c.d->init_hist[0]; c.h1 = c.d->init_hist[1]; c.h2 = c.d->init_hist[2];
+        c.out = seq_scratch + c.d->seq_buf_off * 3;
+        if (!c.bad) {
+            c.logL = c.tl->log; c.logM = c.tm->log; c.logO = c.to->log;
+            const uint32_t aTL = (uint32_t)__cvta_generic_to_shared(TL), aTM = aTL + 1024u, aTO = aTL + 2048u;
+            c.qTL = aTL - (2u << c.logL); c.qTM = aTM - (2u << c.logM); c.qTO = aTO - (2u << c.logO);
+            // initial states LL, OF, ML (sequence_section_decoder.rs:164-166)
+            uint32_t hi, lo;
+            c.br.window(hi, lo);
+            const uint32_t t1 = shl_c(hi, c.logL), t2 = shl_c(t1, c.logO);
+            c.eL = fse_lds16(aTL + (shr_c(hi, 32u - c.logL) << 1));
+            c.eO = fse_lds16(aTO + (shr_c(t1, 32u - c.logO) << 1));
+            c.eM = fse_lds16(aTM + (shr_c(t2, 32u - c.logM) << 1));
+            c.br.P -= (int32_t)(c.logL + c.logO + c.logM);
+        }
+    }
+    // joint loop: groups of four sequences of every chain, step by step in turn
+    {
+        bool joint = true;
+        uint32_t nmin = 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < (int)FSE_CHAINS; k++) { joint = joint && ch[k].run && !ch[k].bad; nmin = min(nmin, ch[k].run ? ch[k].nseq : 0u); }
+        if (FSE_CHAINS > 1 && joint) {
+            uint32_t stage[FSE_CHAINS][12];
+            uint32_t i = 0, anyflag = 0;
+            for (; i + 4 < nmin; i += 4) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+#pragma unroll
+                    for (int k = 0; k < (int)FSE_CHAINS; k++) fse_step(ch[k], qLL, qML, stage[k][3 * q], stage[k][3 * q + 1], stage[k][3 * q + 2], true);
+                    if (q & 1) {
+#pragma unroll
+                        for (int k = 0; k < (int)FSE_CHAINS; k++) ch[k].br.service();
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < (int)FSE_CHAINS; k++) { ch[k].i = i; fse_group_end(ch[k], stage[k]); anyflag |= ch[k].flags; }
+                if (anyflag) { i += 4; break; }
+                if (((i + 4) & 127u) == 0) {   // every 128 sequences: the fence costs ~1 us
+                    __threadfence();
+#pragma unroll
+                    for (int k = 0; k < (int)FSE_CHAINS; k++) asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(&aux[ch[k].b].progress), "r"(i + 4) : "memory");
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < (int)FSE_CHAINS; k++) ch[k].i = i;
+        }
+    }
+    // each chain on its own: the rest of its groups, then its last sequences one at a time
+#pragma unroll
+    for (int k = 0; k < (int)FSE_CHAINS; k++) {
+        FseChain &c = ch[k];
+        if (!c.run || c.bad) continue;
+        if (!c.flags) {
+            uint32_t stage[12];
+            for (; c.i + 4 < c.nseq; c.i += 4) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) { fse_step(c, qLL, qML, stage[3 * q], stage[3 * q + 1], stage[3 * q + 2], true); if (q & 1) c.br.service(); }
+                fse_group_end(c, stage);
+                if (c.flags) break;
+                if (((c.i + 4) & 127u) == 0) fse_publish(aux, c.b, c.i + 4);
+            }
+        }
+        if (!c.flags) {
+            for (; c.i < c.nseq; c.i++) {
+                uint32_t ll, ml, of;
+                fse_step(c, qLL, qML, ll, ml, of, c.i + 1 < c.nseq);
+                c.br.service();
+                c.flags |= (uint32_t)(c.br.P < 0) | (uint32_t)(c.max_x > 32u) | (c.or_of >> 5);
+                c.out[3 * c.i] = ll; c.out[3 * c.i + 1] = ml; c.out[3 * c.i + 2] = of;
+            }
+        }
+        c.bad = c.flags != 0 || c.br.P != 0;
+        if (!c.bad) {
+            aux[c.b].pad = 0;
+            if (c.resolve) { aux[c.b].hist_after[0] = c.h0; aux[c.b].hist_after[1] = c.h1; aux[c.b].hist_after[2] = c.h2; }
+            uint64_t total = c.sum_ml + c.d->regen_size;
+            aux[c.b].out_size = (uint32_t)(total > 0xffffffffull ? 0xffffffffull : total);
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // verdicts; blocks the fast path gave up on are decoded again by the exact path
+#pragma unroll
+    for (int k = 0; k < (int)FSE_CHAINS; k++) {
+        FseChain &c = ch[k];
+        if (!c.active) continue;
+        if (!c.run) { aux[c.b].pad = c.st_seq; fse_publish(aux, c.b, FSE_PROGRESS_FINAL); continue; }
+        if (!c.bad) { fse_publish(aux, c.b, FSE_PROGRESS_FINAL); continue; }
+        const uint16_t *TL = tabs + (FSE_CHAINS * lane + k) * FSE_TAB_U16;
+        fse_exact_block(c.d, aux, c.b, input, seq_scratch, TL, TL + 512, TL + 1024, c.tl, c.to, c.tm, s_ll_base, s_ml_base, s_ll_bits, s_ml_bits, c.st_seq);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1340,7 +1424,7 @@ int launch_predefined(FseSlot *predef, cudaStream_t s) {
 }
 
 constexpr uint32_t kHufSmem = HUF_BLOCKS_PER_CTA * HUF_SMEM_PER_BLOCK + 32 * RING_STRIDE;
-constexpr uint32_t kFseSmem = FSE_BLOCKS_PER_CTA * FSE_TAB_U16 * 2 + 1024 + 32 * RING_STRIDE;
+constexpr uint32_t kFseSmem = FSE_BLOCKS_PER_CTA * FSE_TAB_U16 * 2 + 1024 + FSE_BLOCKS_PER_CTA * RING_STRIDE;
 
 int init_kernels() {
     cudaError_t e = cudaFuncSetAttribute(k_fse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFseSmem);
