@@ -799,6 +799,7 @@ __device__ __noinline__ void fse_exact_block(const BlockDesc *d, BlockAux *aux, 
 
 __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs, BlockAux *__restrict__ aux, const uint8_t *__restrict__ input,
                                           uint32_t *__restrict__ seq_scratch, uint32_t nblocks) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // this CTA is resident: k_exec may follow (launch_pipeline_overlapped)
     extern __shared__ __align__(16) uint8_t smem_fse[];
     uint16_t *tabs = reinterpret_cast<uint16_t *>(smem_fse);
     uint32_t *s_ll_base = reinterpret_cast<uint32_t *>(smem_fse + FSE_BLOCKS_PER_CTA * FSE_TAB_U16 * 2);
@@ -1472,23 +1473,28 @@ int launch_pipeline(const PipelineArgs &a, cudaStream_t s) {
     return 0;
 }
 
-// k_huf and k_fse are independent (literals vs sequences of the same blocks) and both leave most issue slots
-// idle (a few latency-bound warps per SM): run them side by side -- k_huf on the side stream, forked after
-// k_setup and joined before k_exec.
+// k_exec runs beside k_fse and consumes its sequences through the per-block progress counters.  That is only safe if every
+// CTA of k_fse is resident before the first CTA of k_exec takes an SM: a k_exec CTA spins on blocks whose producer may not
+// have been placed yet, and an SM full of spinning consumers has no room for a producer (measured without the guarantee:
+// 4.4 -> 220 ms per pass when the hardware happened to place k_exec first).  Programmatic dependent launch gives exactly
+// that order: k_exec is launched in the same stream as a programmatic dependent of k_fse, whose CTAs all execute
+// griddepcontrol.launch_dependents as their first instruction; k_exec never calls griddepcontrol.wait -- the data hand-off is
+// the progress counters, and everything k_exec reads from k_setup / k_huf completed before k_fse started (stream order).
 int launch_pipeline_overlapped(const PipelineArgs &a, const PipelineStreams &ps) {
-    // main: k_setup -> k_huf -> k_fse.   side (forked after k_huf): k_exec, which consumes sequences while k_fse is still
-    // producing them (per-block progress counters).  k_fse is submitted first and on the high-priority stream, so its
-    // CTAs are always placed before k_exec's.  (k_huf cannot share an SM with k_fse: 2 x 86 KiB + 29 KiB of shared
-    // memory do not fit the carve-out, so it runs before it.)
     int e;
     if ((e = launch_stage(a, 0, ps.main))) return e;
     if ((e = launch_stage(a, 1, ps.main))) return e;
-    if ((e = (int)cudaEventRecord(ps.fork, ps.main))) return e;
     if ((e = launch_stage(a, 2, ps.main))) return e;
-    if ((e = (int)cudaStreamWaitEvent(ps.side, ps.fork, 0))) return e;
-    if ((e = launch_stage(a, 3, ps.side))) return e;
-    if ((e = (int)cudaEventRecord(ps.join, ps.side))) return e;
-    return (int)cudaStreamWaitEvent(ps.main, ps.join, 0);
+    if (!a.nframes) return 0;
+    if (!a.nblocks) return launch_stage(a, 3, ps.main);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cdiv(a.nframes, EXEC_WARPS)); cfg.blockDim = dim3(EXEC_WARPS * 32); cfg.dynamicSmemBytes = 0; cfg.stream = ps.main;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, k_exec, a.descs, (const BlockAux *)a.aux, a.frames, a.states, a.input, (const uint8_t *)a.lit_scratch,
+                                   (const uint32_t *)a.seq_scratch, a.output, a.output_cap, a.nframes);
 }
 
 uint32_t pipeline_launch_count(const PipelineArgs &a) { return (a.nblocks ? 3u : 0u) + (a.nframes ? 1u : 0u); }
