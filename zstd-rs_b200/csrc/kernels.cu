@@ -22,64 +22,6 @@
 namespace b200z {
 
 // ------------------------------------------------------------------------------------------------------------
-// Reversed bit reader over global memory (the device form of BitReaderReversed, bit_reader_reverse.rs:6-162):
-// left-aligned 64-bit container refilled with ALIGNED 32-bit words walking down the stream; bits below the
-// stream start read as zero and `p` (bits remaining) goes negative, like bits_remaining() (:27-29).
-// ------------------------------------------------------------------------------------------------------------
-struct RevBits {
-    const uint32_t *base;  // 4-byte aligned address at or below the stream start
-    uint64_t cont;         // unread bits, left aligned
-    int32_t fill;          // bits loaded in cont (virtual zeros below the stream start count)
-    int32_t wi;            // words [0, wi) not fetched yet
-    uint32_t g0;           // bit offset of the stream's first byte inside word 0
-    int32_t p;             // bits_remaining()
-
-    // Position right below the end-of-stream marker.  Returns false for "ExtraPadding" (no 1 bit in the last
-    // byte, or an empty stream): the callers' skip loops (literals_section_decoder.rs:97-109 etc.) give up
-    // after 8 zero bits.
-    __device__ __forceinline__ bool init(const uint8_t *src, uint32_t len) {
-        if (len == 0) return false;
-        uint32_t last = src[len - 1];
-        if (last == 0) return false;
-        uintptr_t a = (uintptr_t)src;
-        base = (const uint32_t *)(a & ~(uintptr_t)3);
-        g0 = (uint32_t)(a & 3) * 8u;
-        p = (int32_t)((len - 1) * 8u + (31u - (uint32_t)__clz((int)last)));  // data bits below the marker
-        cont = 0; fill = 0; wi = 0;
-        if (p > 0) {
-            uint32_t gtop = g0 + (uint32_t)p - 1u;  // global bit index of the first data bit
-            wi = (int32_t)(gtop >> 5);
-            uint32_t w = __ldg(base + wi);
-            if (wi == 0) w &= ~((1u << g0) - 1u);
-            uint32_t used = (gtop & 31u) + 1u;
-            cont = (uint64_t)w << (64u - used);
-            fill = (int32_t)used;
-        }
-        return true;
-    }
-    __device__ __forceinline__ void refill() {  // afterwards fill > 32
-        if (fill <= 32) {
-            uint32_t w = 0;
-            if (wi > 0) {
-                --wi;
-                w = __ldg(base + wi);
-                if (wi == 0) w &= ~((1u << g0) - 1u);
-            }
-            cont |= (uint64_t)w << (32 - fill);
-            fill += 32;
-        }
-    }
-    __device__ __forceinline__ uint32_t get(uint32_t n) {  // n <= 32, needs fill >= n
-        uint32_t v = (uint32_t)((cont >> 1) >> (63u - n));
-        cont <<= n;
-        fill -= (int32_t)n;
-        p -= (int32_t)n;
-        return v;
-    }
-    __device__ __forceinline__ uint32_t peek(uint32_t n) const { return (uint32_t)((cont >> 1) >> (63u - n)); }
-};
-
-// ------------------------------------------------------------------------------------------------------------
 __global__ void k_predefined(FseSlot *predef) {
     uint32_t k = threadIdx.x;
     if (k < 3) fse_build_predefined(k, k == 0 ? &predef->ll : (k == 1 ? &predef->of : &predef->ml));
@@ -163,9 +105,8 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(const BlockDesc *__r
 
 // ------------------------------------------------------------------------------------------------------------
 // k_huf: literals.  One CTA (one warp) = 8 blocks x 4 streams; the 8 huff0 LUTs (3 KiB each, split symbol /
-// 4-bit length) are staged into shared memory; every lane walks its own reversed bitstream with a 64-bit window
-// refilled by aligned 32-bit words (next word prefetched one refill ahead) and writes its symbols in 16-byte
-// vectors.
+// 4-bit length) are staged into shared memory; every lane walks its own reversed bitstream -- one 64-bit window
+// (PosRing: 3 LDS + 2 funnel shifts) per four symbols -- and writes its symbols in 16-byte vectors.
 // ------------------------------------------------------------------------------------------------------------
 constexpr uint32_t HUF_BLOCKS_PER_CTA = 8;
 constexpr uint32_t HUF_SMEM_PER_BLOCK = HUF_TABLE_ENTRIES + HUF_TABLE_ENTRIES / 2;  // 3072
@@ -176,91 +117,7 @@ __device__ __forceinline__ uint32_t shl_c(uint32_t a, uint32_t n) { uint32_t r; 
 __device__ __forceinline__ uint32_t fsl_c(uint32_t lo, uint32_t hi, uint32_t n) { return __funnelshift_lc(lo, hi, n); }
 __device__ __forceinline__ uint32_t bfind32(uint32_t a) { uint32_t r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(a)); return r; }   // floor(log2 a)
 
-// Reversed bit reader whose words come from a per-lane ring in shared memory (32 words = 8 groups of 16 bytes)
-// that cp.async keeps filled 7 groups ahead of consumption: the refill is two shifts and an LDS, never a global
-// load on the dependency chain.  Branch-free: every operation is predicated, so 32 lanes decoding 32 different
-// blocks stay converged.  Same observable behaviour as BitReaderReversed (bit_reader_reverse.rs:6-162).
-constexpr uint32_t RING_STRIDE = 144;   // bytes per lane: 128 + 16 so that lanes start 4 banks apart
-struct RingBits {
-    const uint4 *base;   // 16-byte aligned address at or below the stream start
-    uint32_t ring;       // shared-memory byte address (cvta) of this lane's ring
-    uint32_t hi, lo;
-    int32_t fill;
-    int32_t wi;          // words [0, wi) not consumed; nextw holds word wi - 1
-    int32_t next_g;      // next group to request (descending); the group being consumed is next_g + 8
-    int32_t sw;
-    uint32_t smask;
-    uint32_t nextw;
-    int32_t p;
-
-    __device__ __forceinline__ void request(int32_t g) {
-        uint32_t dst = ring + (((uint32_t)g & 7u) << 4);
-        const uint4 *src = base + g;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.commit_group;" ::"r"(dst), "l"(src) : "memory");
-    }
-    __device__ __forceinline__ uint32_t lds(uint32_t addr) const { uint32_t w; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr) : "memory"); return w; }
-    __device__ __forceinline__ void sts(uint32_t addr, uint32_t w) const { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(w) : "memory"); }
-    // group 0 holds the stream's first byte: zero what lies below it, once, after it has landed
-    __device__ __forceinline__ void fixup_group0() {
-        for (int32_t i = 0; i <= sw; i++) { uint32_t a = ring + ((uint32_t)i << 2); sts(a, i < sw ? 0u : (lds(a) & smask)); }
-    }
-    __device__ __forceinline__ uint32_t word(int32_t i) const { uint32_t w = lds(ring + (((uint32_t)i & 31u) << 2)); return i >= 0 ? w : 0u; }
-    __device__ __forceinline__ bool init(const uint8_t *src, uint32_t len, uint32_t ring_addr) {
-        ring = ring_addr;
-        hi = lo = 0; fill = 0; wi = 0; next_g = -9; nextw = 0; p = 0; sw = 0; smask = 0; base = nullptr;
-        if (len == 0) return false;
-        uint32_t last = src[len - 1];
-        if (last == 0) return false;
-        uintptr_t a = (uintptr_t)src;
-        base = (const uint4 *)(a & ~(uintptr_t)15);
-        uint32_t g0 = (uint32_t)(a & 15) * 8u;
-        sw = (int32_t)(g0 >> 5);
-        smask = ~((1u << (g0 & 31u)) - 1u);
-        p = (int32_t)((len - 1) * 8u + (31u - (uint32_t)__clz((int)last)));
-        if (p > 0) {
-            uint32_t gtop = g0 + (uint32_t)p - 1u;
-            wi = (int32_t)(gtop >> 5) + 1;
-            int32_t gt = (wi - 1) >> 2;
-            for (int32_t g = gt; g > gt - 8; g--) if (g >= 0) request(g);
-            next_g = gt - 8;
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            if (gt < 8) fixup_group0();
-            uint32_t w = word(wi - 1);
-            wi -= 1;
-            uint32_t used = (gtop & 31u) + 1u;
-            hi = w << (32u - used);
-            fill = (int32_t)used;
-            nextw = word(wi - 1);
-        }
-        return true;
-    }
-    // afterwards fill > 32.  Predicated, no branch, no global access.
-    __device__ __forceinline__ void refill() {
-        const bool need = fill <= 32;
-        const uint32_t w = need ? nextw : 0u;
-        hi |= shr_c(w, (uint32_t)fill);
-        lo |= shl_c(w, 32u - (uint32_t)fill);
-        fill += need ? 32 : 0;
-        wi -= need ? 1 : 0;                       // may run below zero: word() returns 0 there
-        nextw = need ? word(wi - 1) : nextw;
-    }
-    // keeps the ring 7 groups ahead; call at least once per 4 consumed words (once per sequence / per 4 symbols)
-    __device__ __forceinline__ void service() {
-        const int32_t cur_g = (wi - 1) >> 2;             // group of the preloaded word (arithmetic shift: -1 when done)
-        if (cur_g < next_g + 8) {                        // consumption left group next_g + 8: its slot is free
-            if (next_g >= 0) request(next_g);
-            next_g -= 1;
-            asm volatile("cp.async.wait_group 6;" ::: "memory");
-            if (cur_g == 1) fixup_group0();   // group 0 has landed (groups >= cur_g - 1 are complete) and nothing of it was read yet
-        }
-    }
-    __device__ __forceinline__ void skip(uint32_t n) {  // n <= 32
-        hi = fsl_c(lo, hi, n);
-        lo = shl_c(lo, n);
-        fill -= (int32_t)n;
-        p -= (int32_t)n;
-    }
-};
+constexpr uint32_t RING_STRIDE = 144;   // bytes of shared memory per bitstream: a mirror group + 8 groups of 16 bytes (PosRing)
 
 // ---- shared-memory accessors by 32-bit shared address
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
@@ -274,7 +131,7 @@ __device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) { asm 
 __device__ __forceinline__ void red_or_shared(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 
-// Position-based reversed bit reader for k_fse's fast path.  The only state is P = bits_remaining()
+// Position-based reversed bit reader for the fast paths of k_fse and k_huf.  The only state is P = bits_remaining()
 // (bit_reader_reverse.rs:27-29); every read assembles the 64 bits below position P from three words of a per-lane
 // shared-memory ring (8 groups of 16 bytes + a mirror of the top group below slot 0, so that the three words are
 // always at a0, a0 - 4, a0 - 8) that cp.async keeps filled 7 groups ahead of consumption.  No window registers,
@@ -592,10 +449,11 @@ __global__ void __launch_bounds__(32) k_huf(const BlockDesc *__restrict__ descs,
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_fse: sequences.  One lane per block, one warp (32 blocks) per CTA; the 32 x (LL + ML + OF) 16-bit LUTs are
-// staged into shared memory (80 KiB), code -> (baseline, extra bits) comes from two small shared LUTs, the
-// reversed bitstream is read through a 64-bit window with the next aligned word prefetched, and sequences are
-// written four at a time as three 16-byte vectors.
+// k_fse: sequences.  One lane per block, FSE_LANES blocks per one-warp CTA; the (LL + ML + OF) 16-bit LUTs of the
+// CTA's blocks are staged into shared memory (2.5 KiB per block), code -> (baseline, extra bits) comes from two small
+// shared LUTs, the reversed bitstream is read through PosRing (one 64-bit window per sequence), and sequences are
+// written four at a time as three 16-byte vectors.  A warp alone on its scheduler is bound by the 16-lane integer
+// pipe (2 cycles per warp instruction), not by dependencies: the step is written for instruction count.
 // ------------------------------------------------------------------------------------------------------------
 #ifndef B200Z_FSE_CHAINS
 #define B200Z_FSE_CHAINS 1
@@ -963,17 +821,18 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_exec: LZ77 execution.  One warp per frame, blocks in order, 32 sequences per step.
+// k_exec: LZ77 execution.  One warp per frame, blocks in order, 64 sequences per step.
 //
-// Fast path (per batch of 32 sequences, lane j = sequence j): warp scans give every sequence its literal and
-// match positions; a bitmask of match starts in shared memory lets each OUTPUT byte find its owner with one
-// popc; the batch's bytes are then produced row by row (32 consecutive bytes = one coalesced store): literal
-// bytes first, then match bytes whose source byte is final, looping inside the row until it is complete
-// (sources always precede destinations, so the lowest pending byte is always ready).  Overlapping matches use
-// source = start + (k mod offset), the byte-order-preserving form of repeat_in_chunks (decode_buffer.rs:113-141).
-// Anything unusual in a batch (dictionary reach, long runs, zero offsets, literal under-run, capacity) sends
-// that batch to the exact sequential path below, which is execute_sequences / DecodeBuffer::repeat statement by
-// statement.
+// Fast path (per batch of 64 sequences, lane j = sequences 2j and 2j + 1): one warp scan gives every sequence its
+// literal and match positions; a bitmask of sequence ends in shared memory lets each OUTPUT byte find its owner
+// with one popc, an 8-byte record per sequence tells it where it comes from; the batch's bytes are then produced
+// row by row (32 consecutive bytes = one coalesced store), four rows' loads in flight: literal bytes and match
+// bytes whose source is final first, then the few match bytes whose source lies inside the same four rows,
+// looping inside a row until it is complete (sources always precede destinations, so the lowest pending byte is
+// always ready).  Overlapping matches use source = start + (k mod offset), the byte-order-preserving form of
+// repeat_in_chunks (decode_buffer.rs:113-141).  Anything unusual in a batch (dictionary reach, zero offsets,
+// literal under-run, capacity, more than EXEC_TMAX bytes) sends that batch to the exact sequential path below,
+// which is execute_sequences / DecodeBuffer::repeat statement by statement.
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint32_t n, uint32_t lane) {
     for (uint32_t k = lane; k < n; k += 32) dst[k] = src[k];
@@ -1087,9 +946,6 @@ constexpr uint32_t EXEC_BATCH = 64;                         // sequences per bat
 constexpr uint32_t EXEC_TMAX = B200Z_EXEC_TMAX;             // most bytes one batch may produce on the fast path (sizes the end-bit mask)
 #ifndef B200Z_EXEC_CHUNK_ROWS
 #define B200Z_EXEC_CHUNK_ROWS 4
-#endif
-#ifndef B200Z_EXEC_PIPE
-#define B200Z_EXEC_PIPE 0
 #endif
 #ifndef B200Z_EXEC_PREFETCH
 #define B200Z_EXEC_PREFETCH 1
@@ -1253,10 +1109,10 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                 const uint8_t *litq = lit.p + st.litpos;
                 asm volatile("" : "+l"(bout), "+l"(litq));   // keep both bases as single 64-bit registers (one add per access)
                 uint32_t before = 0;   // sequences ended in earlier rows
-                // Rows are produced EXEC_CHUNK_ROWS at a time, software pipelined: the loads of chunk c + 1 (every byte whose
-                // source is final: literals, and matches reaching back past the start of chunk c) are issued before chunk c
-                // is stored, so their latency overlaps the stores and the next chunk's index work; the few bytes whose source
-                // lies inside the chunk being stored or the one in flight follow in the chunk's dependent phase, row by row.
+                // Rows are produced EXEC_CHUNK_ROWS at a time: every byte whose source lies before the chunk (literals, and
+                // matches reaching back past the chunk start) is loaded first -- EXEC_CHUNK_ROWS independent loads per lane in
+                // flight -- then stored; the few bytes whose source lies inside the chunk follow, row by row.  (Issuing the
+                // next chunk's loads before this chunk's stores was measured slower: more bytes turn dependent.)
                 // The per-byte work is branch-free: one select between the literal and the match source.
                 // tag: TAG_NONE = nothing to do, TAG_STORE = value loaded, otherwise the (batch-relative, >= floor) source
                 // position of a match byte that had to wait.
@@ -1310,28 +1166,11 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                     }
                     __syncwarp();
                 };
-#if B200Z_EXEC_PIPE
-                {
-                    uint32_t va[R]; int32_t ta[R];
-                    load_chunk(0, 0, va, ta);
-                    for (uint32_t r0 = 0; r0 < nrows; r0 += R) {
-                        uint32_t vb[R]; int32_t tb[R];
-                        const int32_t floor_a = r0 ? (int32_t)((r0 - R) << 5) : 0;
-#pragma unroll
-                        for (int i = 0; i < R; i++) { vb[i] = 0; tb[i] = TAG_NONE; }
-                        if (r0 + R < nrows) load_chunk(r0 + R, (int32_t)(r0 << 5), vb, tb);
-                        store_chunk(r0, floor_a, va, ta);
-#pragma unroll
-                        for (int i = 0; i < R; i++) { va[i] = vb[i]; ta[i] = tb[i]; }
-                    }
-                }
-#else
                 for (uint32_t r0 = 0; r0 < nrows; r0 += R) {
                     uint32_t va[R]; int32_t ta[R];
                     load_chunk(r0, (int32_t)(r0 << 5), va, ta);
                     store_chunk(r0, (int32_t)(r0 << 5), va, ta);
                 }
-#endif
                 __syncwarp();
                 st.produced += T; st.counter += T; st.litpos += L;
             }
