@@ -240,8 +240,9 @@ int b200z_batch_finish(b200z_batch *b, b200z_frame_result *results);
 /* b200z_batch_run with a CUDA event between kernels: synchronises and returns each kernel's device milliseconds
  * (stage_ms[i] for kernel b200z_stage_kernel_name(i), i < b200z_num_stages()).  Profiling aid for bench.py. */
 int b200z_batch_run_profile(b200z_batch *b, uint8_t *d_output, size_t output_cap, float *stage_ms, size_t nstages);
-/* one overlapped pass exactly as b200z_batch_run launches it, with an event after each kernel on its own stream:
- * out_ms[0..3] = completion times of k_setup, k_huf, k_fse, k_exec relative to the start of the pass (n >= 4) */
+/* one overlapped pass exactly as b200z_batch_run launches it, with an event after k_setup, k_huf and k_exec:
+ * out_ms[0], [1], [3] = their completion times relative to the start of the pass; out_ms[2] = -1 (k_fse runs underneath
+ * k_exec, which is launched as its programmatic dependent: an event between the two would serialise them) (n >= 4) */
 int b200z_batch_run_timeline(b200z_batch *b, uint8_t *d_output, size_t output_cap, float *out_ms, size_t n);
 int b200z_num_stages(void);
 const char *b200z_stage_kernel_name(int stage);

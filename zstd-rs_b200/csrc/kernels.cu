@@ -1323,11 +1323,16 @@ int launch_pipeline_overlapped(const PipelineArgs &a, const PipelineStreams &ps)
     int e;
     if ((e = launch_stage(a, 0, ps.main))) return e;
     if ((e = launch_stage(a, 1, ps.main))) return e;
-    if ((e = launch_stage(a, 2, ps.main))) return e;
+    return launch_fse_exec(a, ps.main);
+}
+
+int launch_fse_exec(const PipelineArgs &a, cudaStream_t s) {
+    int e;
+    if ((e = launch_stage(a, 2, s))) return e;
     if (!a.nframes) return 0;
-    if (!a.nblocks) return launch_stage(a, 3, ps.main);
+    if (!a.nblocks) return launch_stage(a, 3, s);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(cdiv(a.nframes, EXEC_WARPS)); cfg.blockDim = dim3(EXEC_WARPS * 32); cfg.dynamicSmemBytes = 0; cfg.stream = ps.main;
+    cfg.gridDim = dim3(cdiv(a.nframes, EXEC_WARPS)); cfg.blockDim = dim3(EXEC_WARPS * 32); cfg.dynamicSmemBytes = 0; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;

@@ -50,7 +50,16 @@ __device__ int fse_build_warp(SetupScratch &sc, uint32_t nprobs, uint32_t log, u
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += v; }
         uint32_t first = total + incl - cnt;
-        for (uint32_t k = 0; k < cnt && first + k < size; k++) sc.sym_of_rank[first + k] = (uint8_t)s;
+        // short runs by their own lane, the rest of a long run (a dominant symbol owns hundreds of cells) by the whole warp
+        const uint32_t own = cnt < 8u ? cnt : 8u;
+        for (uint32_t k = 0; k < own && first + k < size; k++) sc.sym_of_rank[first + k] = (uint8_t)s;
+        uint32_t big = __ballot_sync(0xffffffffu, cnt > 8u);
+        while (big) {
+            const int j = __ffs((int)big) - 1;
+            big &= big - 1;
+            const uint32_t f = __shfl_sync(0xffffffffu, first, j), c = __shfl_sync(0xffffffffu, cnt, j);
+            for (uint32_t k = 8u + lane; k < c && f + k < size; k += 32) sc.sym_of_rank[f + k] = (uint8_t)(base + (uint32_t)j);
+        }
         total += __shfl_sync(0xffffffffu, incl, 31);
     }
     if (nneg > size || total + nneg != size) return B200Z_ERR_REFERENCE_WOULD_PANIC;  // cannot happen: the parser checked the sum

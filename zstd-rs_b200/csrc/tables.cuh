@@ -41,16 +41,16 @@ struct FwdBits {
     uint32_t idx;  // bits read
     B200Z_HD bool get(uint32_t n, uint32_t &out) {  // n <= 24
         if (len * 8u - idx < n) return false;
-        uint32_t v = 0, got = 0, i = idx;
-        while (got < n) {
-            uint32_t byte = src[i >> 3], sh = i & 7u, take = 8u - sh;
-            if (take > n - got) take = n - got;
-            v |= ((byte >> sh) & ((1u << take) - 1u)) << got;
-            got += take;
-            i += take;
+        out = 0;
+        if (n) {   // the n bits starting at bit idx, LSB first: at most 4 bytes, all inside the slice
+            const uint32_t b0 = idx >> 3, sh = idx & 7u, nbytes = (sh + n + 7u) >> 3;
+            uint32_t w = src[b0];
+            if (nbytes > 1) w |= (uint32_t)src[b0 + 1] << 8;
+            if (nbytes > 2) w |= (uint32_t)src[b0 + 2] << 16;
+            if (nbytes > 3) w |= (uint32_t)src[b0 + 3] << 24;
+            out = (w >> sh) & ((1u << n) - 1u);
         }
         idx += n;
-        out = v;
         return true;
     }
 };
@@ -60,12 +60,22 @@ struct FwdBits {
 struct RevBitsSmall {
     const uint8_t *src;
     int32_t p;  // bits remaining (may go negative)
-    B200Z_HD uint32_t get(uint32_t n) {  // n <= 16
+    B200Z_HD uint32_t get(uint32_t n) {  // n <= 16: bits [p - n, p) of the slice read as one little-endian number, bit p - 1 first
         uint32_t v = 0;
-        for (uint32_t k = 0; k < n; k++) {
-            int32_t bit = p - 1 - (int32_t)k;
-            uint32_t b = bit >= 0 ? ((src[bit >> 3] >> (bit & 7)) & 1u) : 0u;
-            v = (v << 1) | b;
+        if (n && p > 0) {
+            const int32_t lo = p - (int32_t)n;
+            if (lo >= 0) {
+                const uint32_t b0 = (uint32_t)lo >> 3, sh = (uint32_t)lo & 7u, nbytes = (sh + n + 7u) >> 3;   // <= 3 bytes
+                uint32_t w = src[b0];
+                if (nbytes > 1) w |= (uint32_t)src[b0 + 1] << 8;
+                if (nbytes > 2) w |= (uint32_t)src[b0 + 2] << 16;
+                v = (w >> sh) & ((1u << n) - 1u);
+            } else {   // only p (< n) real bits are left; zeros below bit 0
+                const uint32_t m = (uint32_t)p;
+                uint32_t w = src[0];
+                if (m > 8) w |= (uint32_t)src[1] << 8;
+                v = (w & ((1u << m) - 1u)) << (n - m);
+            }
         }
         p -= (int32_t)n;
         return v;
