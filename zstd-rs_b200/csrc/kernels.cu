@@ -854,13 +854,24 @@ struct LitSrc { const uint8_t *p; uint32_t rle; uint8_t byte; uint32_t regen; };
 
 // exact sequential execution of up to 32 sequences held one per lane (my_ll/my_ml/my_of); `resolved` = offsets
 // already went through do_offset_history.  Returns 0 or an error code.
-// Sequence j of the batch lives in lane j >> 1, slot j & 1 (two records per lane: a = even, b = odd).
-__device__ uint32_t exec_batch_exact(ExecState &st, const LitSrc &lit, const FrameDesc &fd, uint8_t *out, uint32_t nb, uint32_t ll_a, uint32_t ml_a,
-                                     uint32_t of_a, uint32_t ll_b, uint32_t ml_b, uint32_t of_b, bool resolved, uint32_t lane) {
+#ifndef B200Z_EXEC_PER_LANE
+#define B200Z_EXEC_PER_LANE 2
+#endif
+constexpr uint32_t EXEC_PER_LANE = B200Z_EXEC_PER_LANE;      // consecutive sequences a lane holds (even)
+constexpr uint32_t EXEC_BATCH = 32 * EXEC_PER_LANE;         // sequences per batch
+// Sequence j of the batch lives in lane j / EXEC_PER_LANE, slot j % EXEC_PER_LANE.
+__device__ __forceinline__ uint32_t exec_pick(const uint32_t (&v)[EXEC_PER_LANE], uint32_t slot) {
+    uint32_t r = v[0];
+#pragma unroll
+    for (uint32_t k = 1; k < EXEC_PER_LANE; k++) r = slot == k ? v[k] : r;
+    return r;
+}
+__device__ uint32_t exec_batch_exact(ExecState &st, const LitSrc &lit, const FrameDesc &fd, uint8_t *out, uint32_t nb, const uint32_t (&lls)[EXEC_PER_LANE],
+                                     const uint32_t (&mls)[EXEC_PER_LANE], const uint32_t (&ofs)[EXEC_PER_LANE], bool resolved, uint32_t lane) {
     for (uint32_t j = 0; j < nb; j++) {
-        const bool odd = (j & 1u) != 0;
-        uint32_t ll = __shfl_sync(0xffffffffu, odd ? ll_b : ll_a, j >> 1), ml = __shfl_sync(0xffffffffu, odd ? ml_b : ml_a, j >> 1),
-                 of = __shfl_sync(0xffffffffu, odd ? of_b : of_a, j >> 1);
+        const uint32_t slot = j % EXEC_PER_LANE, src_lane = j / EXEC_PER_LANE;
+        uint32_t ll = __shfl_sync(0xffffffffu, exec_pick(lls, slot), src_lane), ml = __shfl_sync(0xffffffffu, exec_pick(mls, slot), src_lane),
+                 of = __shfl_sync(0xffffffffu, exec_pick(ofs, slot), src_lane);
         if (ll > 0) {
             if ((uint64_t)st.litpos + ll > lit.regen) return B200Z_ERR_EXEC_NOT_ENOUGH_BYTES_FOR_SEQUENCE;
             if (st.produced + ll > st.cap) return B200Z_ERR_TARGET_TOO_SMALL;
@@ -939,7 +950,6 @@ __device__ __forceinline__ uint32_t exec_wait_progress(const BlockAux *aux, uint
 #define B200Z_EXEC_WARPS 4
 #endif
 constexpr uint32_t EXEC_WARPS = B200Z_EXEC_WARPS;
-constexpr uint32_t EXEC_BATCH = 64;                         // sequences per batch: two per lane
 #ifndef B200Z_EXEC_TMAX
 #define B200Z_EXEC_TMAX 8128
 #endif
@@ -1019,8 +1029,9 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
             const bool resolved = resolved_u != 0;
             __syncwarp();
             // sequence records stream in from k_fse, which may still be decoding this block: `avail` = published count.
-            // A batch is 64 sequences, two per lane (2 * lane and 2 * lane + 1: 24 contiguous bytes); the next batch's
-            // records are requested into L2 one batch ahead.
+            // A batch is EXEC_BATCH sequences, EXEC_PER_LANE consecutive ones per lane (contiguous 12-byte records); the next
+            // batch's records are requested into L2 one batch ahead.
+            constexpr uint32_t K = EXEC_PER_LANE;
             uint32_t avail = 0;
             for (uint32_t base = 0; base < nseq_u && !e; base += EXEC_BATCH) {
                 const uint32_t nb = nseq_u - base < EXEC_BATCH ? nseq_u - base : EXEC_BATCH;
@@ -1028,44 +1039,71 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                     avail = exec_wait_progress(aux, b, base + nb, lane);
                     if (avail == 0xFFFFFFFEu) { e = B200Z_ERR_CUDA; break; }
                 }
-                uint32_t ll_a = 0, ml_a = 0, of_a = 1, ll_b = 0, ml_b = 0, of_b = 1;
-                const bool on_a = 2u * lane < nb, on_b = 2u * lane + 1u < nb;
+                uint32_t lls[K], mls[K], ofs[K];
+                bool on[K];
                 {
-                    const uint32_t *sp = seqs + (uint64_t)(base + 2u * lane) * 3;
-                    if (on_b) {
-                        const uint2 r0 = ld_cg_u32x2(sp), r1 = ld_cg_u32x2(sp + 2), r2 = ld_cg_u32x2(sp + 4);
-                        ll_a = r0.x; ml_a = r0.y; of_a = r1.x; ll_b = r1.y; ml_b = r2.x; of_b = r2.y;
-                    } else if (on_a) { ll_a = ld_cg_u32(sp); ml_a = ld_cg_u32(sp + 1); of_a = ld_cg_u32(sp + 2); }
-                    if (base + EXEC_BATCH < nseq_u && lane * 128u < (nseq_u - base - EXEC_BATCH) * 12u && lane < 6u) prefetch_l2(reinterpret_cast<const uint8_t *>(seqs + (uint64_t)(base + EXEC_BATCH) * 3) + lane * 128u);
+                    const uint32_t *sp = seqs + (uint64_t)(base + K * lane) * 3;
+                    uint32_t raw[3 * K];
+                    if (K * lane + K <= nb) {   // all my records exist: K * 12 contiguous bytes, 8-byte aligned
+#pragma unroll
+                        for (uint32_t k = 0; k < 3 * K; k += 2) { const uint2 r = ld_cg_u32x2(sp + k); raw[k] = r.x; raw[k + 1] = r.y; }
+                    } else {
+#pragma unroll
+                        for (uint32_t k = 0; k < K; k++) {
+                            const bool have = K * lane + k < nb;
+                            raw[3 * k] = have ? ld_cg_u32(sp + 3 * k) : 0u; raw[3 * k + 1] = have ? ld_cg_u32(sp + 3 * k + 1) : 0u; raw[3 * k + 2] = have ? ld_cg_u32(sp + 3 * k + 2) : 1u;
+                        }
+                    }
+#pragma unroll
+                    for (uint32_t k = 0; k < K; k++) { on[k] = K * lane + k < nb; lls[k] = raw[3 * k]; mls[k] = raw[3 * k + 1]; ofs[k] = raw[3 * k + 2]; }
+                    if (base + EXEC_BATCH < nseq_u && lane * 128u < (nseq_u - base - EXEC_BATCH) * 12u && lane * 128u < EXEC_BATCH * 12u)
+                        prefetch_l2(reinterpret_cast<const uint8_t *>(seqs + (uint64_t)(base + EXEC_BATCH) * 3) + lane * 128u);
                 }
-                // inclusive scans of ll and ll + ml over the lane pairs
-                uint32_t lit_end = ll_a + ll_b, out_end = ll_a + ml_a + ll_b + ml_b;
+                // inclusive scans of ll and ll + ml over the lanes' groups
+                uint32_t lit_end = 0, out_end = 0;
+#pragma unroll
+                for (uint32_t k = 0; k < K; k++) { lit_end += lls[k]; out_end += lls[k] + mls[k]; }
 #pragma unroll
                 for (int dd = 1; dd < 32; dd <<= 1) {
                     uint32_t a = __shfl_up_sync(0xffffffffu, lit_end, dd), c = __shfl_up_sync(0xffffffffu, out_end, dd);
                     if ((int)lane >= dd) { lit_end += a; out_end += c; }
                 }
                 const uint32_t T = __shfl_sync(0xffffffffu, out_end, 31), L = __shfl_sync(0xffffffffu, lit_end, 31);
-                const uint32_t out_end_b = out_end, out_end_a = out_end - ll_b - ml_b;      // inclusive ends of my two sequences
-                const uint32_t m_start_a = out_end_a - ml_a, m_start_b = out_end_b - ml_b;  // batch-relative starts of my matches
+                // per sequence: inclusive end of its bytes, start of its match, inclusive end of its literals (all batch-relative)
+                uint32_t oend[K], mstart[K], lend[K];
+                {
+                    uint32_t oe = out_end, le = lit_end;
+#pragma unroll
+                    for (int k = (int)K - 1; k >= 0; k--) { oend[k] = oe; lend[k] = le; mstart[k] = oe - mls[k]; oe -= lls[k] + mls[k]; le -= lls[k]; }
+                }
                 // offsets for the fast path must be resolved: blocks whose history is not a plan-time constant resolve here
-                uint32_t off_a = of_a, off_b = of_b;
+                uint32_t offs[K];
+#pragma unroll
+                for (uint32_t k = 0; k < K; k++) offs[k] = ofs[k];
                 uint32_t h0 = st.h0, h1 = st.h1, h2 = st.h2;
                 if (!resolved) {
                     // cheap scalar steps (sequence_execution.rs:59-118); committed only if the fast path is taken (the exact path
                     // redoes the steps itself)
                     for (uint32_t j = 0; j < nb; j++) {
-                        const bool odd = (j & 1u) != 0;
-                        uint32_t ll = __shfl_sync(0xffffffffu, odd ? ll_b : ll_a, j >> 1), of = __shfl_sync(0xffffffffu, odd ? of_b : of_a, j >> 1);
+                        const uint32_t slot = j % K, src_lane = j / K;
+                        uint32_t ll = __shfl_sync(0xffffffffu, exec_pick(lls, slot), src_lane), of = __shfl_sync(0xffffffffu, exec_pick(ofs, slot), src_lane);
                         uint32_t actual = offset_history_step(of, ll, h0, h1, h2);
-                        if (lane == (j >> 1)) { if (odd) off_b = actual; else off_a = actual; }
+                        if (lane == src_lane) {
+#pragma unroll
+                            for (uint32_t k = 0; k < K; k++) offs[k] = slot == k ? actual : offs[k];
+                        }
                     }
                 }
                 const uint64_t reach = st.produced - st.drained;   // bytes of earlier output a match may reach back into
-                const bool ok = (!on_a || (off_a != 0 && (uint64_t)off_a <= reach + m_start_a)) && (!on_b || (off_b != 0 && (uint64_t)off_b <= reach + m_start_b));
+                bool ok = true, ovl = false;
+#pragma unroll
+                for (uint32_t k = 0; k < K; k++) {
+                    ok = ok && (!on[k] || (offs[k] != 0 && (uint64_t)offs[k] <= reach + mstart[k]));
+                    ovl = ovl || offs[k] < mls[k];
+                }
                 const bool fast = __all_sync(0xffffffffu, ok) && T <= EXEC_TMAX && (uint64_t)st.litpos + L <= lit.regen && st.produced + T <= st.cap && !lit.rle;
                 if (!fast) {
-                    e = exec_batch_exact(st, lit, fd, out, nb, ll_a, ml_a, of_a, ll_b, ml_b, of_b, resolved, lane);
+                    e = exec_batch_exact(st, lit, fd, out, nb, lls, mls, ofs, resolved, lane);
                     continue;
                 }
                 if (!resolved) { st.h0 = h0; st.h1 = h1; st.h2 = h2; }
@@ -1073,21 +1111,17 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                 // Sequence j owns the bytes [lit_begin_j, out_end_j): its literal run, then its match.  A bit is set at
                 // the last byte of every sequence, so the owner of output byte q is the number of set bits below q;
                 // one 8-byte shared-memory record per sequence then tells the byte where it comes from.
-                const uint32_t lit_end_a = lit_end - ll_b;
-                const uint32_t m_before_a = m_start_a - lit_end_a, m_before_b = m_start_b - lit_end;   // match bytes of the earlier sequences
                 const uint32_t nrows = (T + 31) >> 5;
                 // The batch's match sources are scattered over the frame's window, and with thousands of frames in flight the
                 // windows do not stay in L2: ask for the sectors now, a few hundred instructions before the rows need them.
                 if (B200Z_EXEC_PREFETCH) {
-                    if (on_a) {
-                        const uint8_t *src = out + st.produced + m_start_a - off_a;
-                        prefetch_l2(src);
-                        if ((((uint32_t)(uintptr_t)src) & 31u) + ml_a > 32u) prefetch_l2(src + ml_a - 1);
-                    }
-                    if (on_b) {
-                        const uint8_t *src = out + st.produced + m_start_b - off_b;
-                        prefetch_l2(src);
-                        if ((((uint32_t)(uintptr_t)src) & 31u) + ml_b > 32u) prefetch_l2(src + ml_b - 1);
+#pragma unroll
+                    for (uint32_t k = 0; k < K; k++) {
+                        if (on[k]) {
+                            const uint8_t *src = out + st.produced + mstart[k] - offs[k];
+                            prefetch_l2(src);
+                            if ((((uint32_t)(uintptr_t)src) & 31u) + mls[k] > 32u) prefetch_l2(src + mls[k] - 1);
+                        }
                     }
                     if (lane == 31) {
                         const uint32_t ahead = st.litpos + L + 256u;   // the literal stream is sequential: stay two lines ahead
@@ -1097,13 +1131,17 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                 sts32(a_mask + (lane << 2), 0u);
                 if (nrows > 32u - EXEC_CHUNK_ROWS)
                     for (uint32_t w = lane + 32; w < ((nrows + EXEC_CHUNK_ROWS - 1u) & ~(EXEC_CHUNK_ROWS - 1u)); w += 32) sts32(a_mask + (w << 2), 0u);
-                // 8-byte record: literal byte q of the sequence is literal number (q - m_before) of the batch, match byte q
-                // comes from output position q - offset (m_start, m_before <= EXEC_TMAX: 16 bits each)
-                sts128(a_recs + (lane << 4), m_start_a | (m_before_a << 16), off_a, m_start_b | (m_before_b << 16), off_b);
-                const bool has_ovl = __any_sync(0xffffffffu, off_a < ml_a || off_b < ml_b);   // some match overlaps its own output (rare)
+                // 8-byte record: literal byte q of the sequence is literal number (q - m_before) of the batch (m_before = match bytes
+                // of the earlier sequences = match start - literal end), match byte q comes from output position q - offset
+                // (m_start, m_before <= EXEC_TMAX: 16 bits each)
+#pragma unroll
+                for (uint32_t k = 0; k < K; k += 2)
+                    sts128(a_recs + ((K * lane + k) << 3), mstart[k] | ((mstart[k] - lend[k]) << 16), offs[k], mstart[k + 1] | ((mstart[k + 1] - lend[k + 1]) << 16), offs[k + 1]);
+                const bool has_ovl = __any_sync(0xffffffffu, ovl);   // some match overlaps its own output (rare)
                 __syncwarp();
-                if (on_a) red_or_shared(a_mask + (((out_end_a - 1) >> 5) << 2), 1u << ((out_end_a - 1) & 31u));
-                if (on_b) red_or_shared(a_mask + (((out_end_b - 1) >> 5) << 2), 1u << ((out_end_b - 1) & 31u));
+#pragma unroll
+                for (uint32_t k = 0; k < K; k++)
+                    if (on[k]) red_or_shared(a_mask + (((oend[k] - 1) >> 5) << 2), 1u << ((oend[k] - 1) & 31u));
                 __syncwarp();
                 uint8_t *bout = out + st.produced;
                 const uint8_t *litq = lit.p + st.litpos;
