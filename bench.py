@@ -312,7 +312,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": int(Cb), "d2h_bytes_per_step": int(D), "ms_per_step": float(te.item()),
                     "call": "b200z_decode_frames_batch with pinned host input/output"},
         }
-        if not args.skip_cpu:
+        if not args.skip_cpu and world == 1:   # the CPU baseline is a single-GPU-run companion (rank 0, N = 1 only)
             line["cpu_baseline"] = cpu_baseline(fs)
         print(json.dumps(line))
     barrier()
