@@ -1123,7 +1123,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                             if ((((uint32_t)(uintptr_t)src) & 31u) + mls[k] > 32u) prefetch_l2(src + mls[k] - 1);
                         }
                     }
-                    if (lane == 31) {
+                    if (lane == 31 && lit.regen) {
                         const uint32_t ahead = st.litpos + L + 256u;   // the literal stream is sequential: stay two lines ahead
                         prefetch_l2(lit.p + (ahead < lit.regen ? ahead : lit.regen - 1));
                     }
