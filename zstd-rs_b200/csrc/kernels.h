@@ -28,7 +28,7 @@ extern const char *const kStageNames[kNumStages];
 int launch_stage(const PipelineArgs &a, int stage, cudaStream_t s);
 int launch_pipeline(const PipelineArgs &a, cudaStream_t s);
 int launch_checksum(const PipelineArgs &a, cudaStream_t s);   // optional 5th stage: XXH64 of every frame's plaintext
-struct PipelineStreams { cudaStream_t main, side; cudaEvent_t fork, join; };
+struct PipelineStreams { cudaStream_t main, side; cudaEvent_t fork, join; };   // only `main` is used since k_exec became a programmatic dependent of k_fse
 int launch_pipeline_overlapped(const PipelineArgs &a, const PipelineStreams &ps);   // k_exec beside k_fse (programmatic dependent launch)
 int launch_fse_exec(const PipelineArgs &a, cudaStream_t s);                          // the overlapped pair alone
 uint32_t pipeline_launch_count(const PipelineArgs &a);
