@@ -15,3 +15,17 @@ def test_description_bit_readers_match_bit_serial_reference(tmp_path):
     subprocess.check_call([nvcc, "-x", "cu", "-std=c++17", "-O2", "-w", "-o", exe, os.path.join(HERE, "host", "bit_readers_test.cpp")])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout + out.stderr
+
+
+def test_bench_reference_arm_line(tmp_path):
+    """`bench.py --impl reference` (the restated CPU path on the host cores) prints the contract's JSON line on a small workload."""
+    import json
+    import sys
+    root = os.path.dirname(HERE)
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--frames", "64", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "decompressed_GBps" and line["unit"] == "GB/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
