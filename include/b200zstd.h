@@ -253,6 +253,10 @@ int b200z_batch_info(const b200z_batch *b, uint64_t out[8]);
  * scratch of the LAST run, laid out exactly as the oracle's trace (oracle/ruzstd_oracle.h zo_block_trace) */
 int b200z_batch_debug_literals(b200z_batch *b, uint32_t block, uint8_t *host_out, size_t cap, size_t *len);
 int b200z_batch_debug_sequences(b200z_batch *b, uint32_t block, uint32_t *host_out_ll_ml_of, size_t cap_seqs, size_t *nseq);
+/* bit 0: the block's `of` column holds raw offset_values; otherwise offsets after do_offset_history
+ * (sequence_execution.rs:59-118), symbolic where they depend on the repeat-offset history at the block's start:
+ * tag << 30 | decrements, tag 1..3 = history slot + 1 */
+int b200z_batch_debug_block_flags(b200z_batch *b, uint32_t block, uint32_t *flags);
 void b200z_batch_destroy(b200z_batch *b);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -11,6 +11,15 @@ from conftest import read_golden
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["cta", "warp"])
+def exec_mode(request, monkeypatch):
+    """Which LZ77 execution kernel takes the frames: k_exec_cta (block assembled in shared memory, falls back to the warp kernel
+    per block for what it does not handle) or k_exec (one warp per frame) for everything.  Tests without this fixture run the
+    shipped default (auto: by frame size / dictionary)."""
+    monkeypatch.setenv("B200Z_EXEC_MODE", request.param)
+    return request.param
+
+
 def _io(pkg, frames, sizes, slack=0):
     io = np.zeros(len(frames), dtype=pkg.binding.FRAME_IO_DTYPE)
     so = oo = 0
@@ -20,7 +29,7 @@ def _io(pkg, frames, sizes, slack=0):
     return io, np.frombuffer(b"".join(frames), dtype=np.uint8), oo
 
 
-def test_corpus_frame_decoder(pkg, ctx, manifest):
+def test_corpus_frame_decoder(pkg, ctx, manifest, exec_mode):
     """tests/decode_corpus.rs through the FrameDecoder mirror: reset + decode_blocks(All) + collect."""
     dec = pkg.FrameDecoder(ctx)
     for name, m in manifest["corpus"].items():
@@ -35,7 +44,7 @@ def test_corpus_frame_decoder(pkg, ctx, manifest):
         assert dec.is_finished()
 
 
-def test_corpus_batch_and_intermediates(pkg, ctx, oracle, manifest):
+def test_corpus_batch_and_intermediates(pkg, ctx, oracle, manifest, exec_mode):
     """All 101 frames in ONE submission; per-block literals and sequences against the oracle's trace."""
     names = sorted(manifest["corpus"])
     frames = [read_golden("decodecorpus", n) for n in names]
@@ -59,6 +68,7 @@ def test_corpus_batch_and_intermediates(pkg, ctx, oracle, manifest):
         r = d.reset(frames[i]); d.decode_blocks(r); d.collect()
         blocks, lits, seqs = d.trace()
         assert res[i]["blocks_decoded"] == len(blocks)
+        hist = [1, 4, 8]   # repeat-offset history at the start of the block (scratch.rs:44)
         for tb in blocks:
             if tb["block_type"] == 2:
                 if tb["literals_type"] >= 2:
@@ -69,10 +79,18 @@ def test_corpus_batch_and_intermediates(pkg, ctx, oracle, manifest):
                     got_s = b.debug_sequences(blk)
                     exp = seqs[tb["seq_offset"]:tb["seq_offset"] + tb["num_sequences"]]
                     assert np.array_equal(got_s[:, :2], exp[:, :2]), (n, blk)
-                    # offsets: raw offset_value, or -- for the first block with sequences of a frame, whose repeat-offset
-                    # history is a plan-time constant -- already through do_offset_history (oracle column 3)
-                    assert np.array_equal(got_s[:, 2], exp[:, 2]) or np.array_equal(got_s[:, 2], exp[:, 3]), (n, blk)
+                    # offsets: raw offset_values when the block went through k_fse's exact path, otherwise already through
+                    # do_offset_history (oracle column 3), symbolic where they depend on the history at the block's start
+                    if b.debug_block_flags(blk) & 1:
+                        assert np.array_equal(got_s[:, 2], exp[:, 2]), (n, blk)
+                    else:
+                        sym = got_s[:, 2].astype(np.int64)
+                        tag, dec = sym >> 30, sym & ((1 << 30) - 1)
+                        h = np.array([0] + hist, dtype=np.int64)[tag]
+                        actual = np.where(tag == 0, sym, np.maximum(h - dec, 0))
+                        assert np.array_equal(actual, exp[:, 3].astype(np.int64)), (n, blk)
                     nseq += len(exp)
+                    hist = list(tb["offset_hist_after"])
             blk += 1
     assert nlit > 1000 and nseq > 1_000_000   # 2458 compressed blocks / 1,031,936 sequences in the corpus
 
@@ -149,7 +167,7 @@ def test_dictionary_kat(pkg, ctx):
             pkg.Dictionary.decode_dict(ctx, raw[:cut])
 
 
-def test_fuzz_artifacts_status_parity(pkg, ctx, oracle, manifest):
+def test_fuzz_artifacts_status_parity(pkg, ctx, oracle, manifest, exec_mode):
     """tests/fuzz_regressions.rs: must not crash; and the GPU path must report the SAME outcome as the oracle
     (same error leaf + stage, or the same bytes)."""
     zo, bz = oracle.error_names(), pkg.error_names()
@@ -179,7 +197,7 @@ def test_fuzz_artifacts_status_parity(pkg, ctx, oracle, manifest):
                 assert exp_err is not None and bz[e.code].replace("B200Z_", "") == exp_err[0], (sub, f, e, exp_err)
 
 
-def test_fuzz_artifacts_without_dict_id(pkg, ctx, oracle, manifest):
+def test_fuzz_artifacts_without_dict_id(pkg, ctx, oracle, manifest, exec_mode):
     """Most artifacts stop at DictNotProvided; clear the dict-id flag so the block path itself sees hostile input."""
     zo, bz = oracle.error_names(), pkg.error_names()
     n = 0
@@ -208,7 +226,7 @@ def test_fuzz_artifacts_without_dict_id(pkg, ctx, oracle, manifest):
     assert n >= 25
 
 
-def test_window_fixtures(pkg, ctx, manifest):
+def test_window_fixtures(pkg, ctx, manifest, exec_mode):
     """tests/mod.rs:576-741."""
     fox = b"The quick brown fox jumps over the lazy dog.\n" * 4096
     sphinx = b"Sphinx of black quartz, judge my vow.\n" * 4096
@@ -291,7 +309,7 @@ def test_api_incremental_read(pkg, ctx):
     assert d.collect_to_writer(w) == 3 and bytes(w.buf) == b"def"
 
 
-def test_api_decode_all(pkg, ctx, manifest):
+def test_api_decode_all(pkg, ctx, manifest, exec_mode):
     """tests/mod.rs:490-574."""
     def skip(n):
         return (0x184D2A50).to_bytes(4, "little") + n.to_bytes(4, "little") + bytes(n)
@@ -315,7 +333,7 @@ def test_api_decode_all(pkg, ctx, manifest):
     assert names[e.value.code] == "B200Z_ERR_FAILED_TO_SKIP_FRAME"
 
 
-def test_strategies_match_oracle(pkg, ctx, oracle):
+def test_strategies_match_oracle(pkg, ctx, oracle, exec_mode):
     """decode_blocks(UptoBlocks / UptoBytes) stop at the same block boundaries and expose the same counters."""
     data = read_golden("decodecorpus", "z000033.zst")
     for strat, n in [(pkg.UPTO_BLOCKS, 7), (pkg.UPTO_BYTES, 5000), (pkg.UPTO_BLOCKS, 0), (pkg.UPTO_BYTES, 300000)]:
@@ -334,7 +352,7 @@ def test_strategies_match_oracle(pkg, ctx, oracle):
         assert a.get_calculated_checksum() == b.get_calculated_checksum()
 
 
-def test_synthetic_configs_small(pkg, ctx, oracle):
+def test_synthetic_configs_small(pkg, ctx, oracle, exec_mode):
     """Small instances of every BASELINE.json config against the oracle AND libzstd."""
     import datagen as G
     sets = [
@@ -419,7 +437,7 @@ def test_irregular_huffman_split_matches_reference_semantics(pkg, ctx, oracle):
             assert (bz[int(res[0]["status"])].replace("B200Z_", ""), int(res[0]["stage"])) == e_err
 
 
-def test_target_too_small_and_capacity_isolation(pkg, ctx):
+def test_target_too_small_and_capacity_isolation(pkg, ctx, exec_mode):
     """A frame that does not fit its out_cap fails alone and never writes past its slot (checked on the device buffer)."""
     import torch
     import datagen as G
@@ -440,7 +458,7 @@ def test_target_too_small_and_capacity_isolation(pkg, ctx):
     assert (out[fs.D:] == 0xAB).all()
 
 
-def test_truncation_sweep_matches_oracle(pkg, ctx, oracle):
+def test_truncation_sweep_matches_oracle(pkg, ctx, oracle, exec_mode):
     """Every prefix of a small frame: same outcome (bytes or error leaf + stage) as the oracle."""
     data = read_golden("decodecorpus", "z000002.zst")
     zo, bz = oracle.error_names(), pkg.error_names()
@@ -460,7 +478,7 @@ def test_truncation_sweep_matches_oracle(pkg, ctx, oracle):
             assert (bz[int(res[i]["status"])].replace("B200Z_", ""), int(res[i]["stage"])) == err, (cuts[i], res[i], err)
 
 
-def test_bitflip_sweep_matches_oracle(pkg, ctx, oracle):
+def test_bitflip_sweep_matches_oracle(pkg, ctx, oracle, exec_mode):
     """Single-bit corruptions of a compressed block: same outcome as the oracle, no device fault."""
     data = bytearray(read_golden("decodecorpus", "z000005.zst"))
     rng = np.random.Generator(np.random.PCG64(11))
@@ -494,7 +512,7 @@ def test_bitflip_sweep_matches_oracle(pkg, ctx, oracle):
     assert same > 0
 
 
-def test_exec_run_shapes(pkg, ctx, oracle):
+def test_exec_run_shapes(pkg, ctx, oracle, exec_mode):
     """Sequence shapes that steer k_exec's batch paths: overlapping matches (offset < length, incl. offset 1), matches and literal
     runs far longer than a row, batches above the fast path's byte cap, odd sequence counts, repeat offsets after zero literal
     lengths.  Bit-exact against the plaintext and the oracle."""

@@ -99,6 +99,7 @@ def lib():
         "b200z_batch_info": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
         "b200z_batch_debug_literals": (C.c_int, [vp, C.c_uint32, vp, sz, C.POINTER(sz)]),
         "b200z_batch_debug_sequences": (C.c_int, [vp, C.c_uint32, vp, sz, C.POINTER(sz)]),
+        "b200z_batch_debug_block_flags": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_uint32)]),
         "b200z_batch_destroy": (None, [vp]),
         "b200z_frame_decoder_new": (C.c_int, [vp, pp]),
         "b200z_frame_decoder_free": (None, [vp]),
@@ -324,7 +325,7 @@ class Batch:
         op, ol, _k = _ptr(d_output)
         ms = (C.c_float * 4)()
         self.ctx._chk(self.ctx.L.b200z_batch_run_timeline(self.h, op, ol, ms, 4))
-        return {"k_setup": float(ms[0]), "k_huf": float(ms[1]), "k_fse": float(ms[2]), "k_exec": float(ms[3])}
+        return {"k_setup": float(ms[0]), "k_huf||k_fse": float(ms[1]), "k_exec_cta": float(ms[2]), "k_exec": float(ms[3])}
 
     def finish(self):
         res = np.zeros(len(self.frames), dtype=FRAME_RESULT_DTYPE)
@@ -348,6 +349,11 @@ class Batch:
         n = C.c_size_t()
         self.ctx._chk(self.ctx.L.b200z_batch_debug_sequences(self.h, block, buf.ctypes.data, cap, C.byref(n)))
         return buf[:n.value].copy()
+
+    def debug_block_flags(self, block):
+        v = C.c_uint32()
+        self.ctx._chk(self.ctx.L.b200z_batch_debug_block_flags(self.h, block, C.byref(v)))
+        return v.value
 
     def close(self):
         if getattr(self, "h", None) and self.ctx.h:

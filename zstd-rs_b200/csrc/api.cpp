@@ -248,7 +248,8 @@ struct Submission {
     std::vector<CarrySet> carries;   // TabRef::CARRY idx -> device tables (dictionaries / streaming carry)
     uint32_t n_huf = 0, n_fse = 0;
     uint64_t lit_bytes = 0, nseq = 0;
-    DevBuf d_descs, d_aux, d_frames, d_states, d_huf, d_fse, d_lit, d_seq;
+    DevBuf d_descs, d_aux, d_frames, d_states, d_huf, d_fse, d_lit, d_seq, d_sched;
+    std::vector<uint32_t> cta_frames;   // frames executed by k_exec_cta (the rest: k_exec, one warp per frame)
 
     void clear() {
         descs.clear(); refs.clear(); frames.clear(); states.clear(); carries.clear();
@@ -266,6 +267,22 @@ struct Submission {
         if ((e = d_fse.ensure((size_t)n_fse * sizeof(FseSlot)))) return e;
         if ((e = d_lit.ensure(lit_bytes + 64))) return e;
         if ((e = d_seq.ensure((nseq + 4) * 12))) return e;
+        // which execution kernel takes a frame: k_exec_cta assembles blocks in shared memory with a whole CTA -- right for
+        // anything but tiny frames; frames with a dictionary stay with the warp kernel (dictionary reach is its exact path).
+        // B200Z_EXEC_MODE = warp | cta | auto (default) overrides for tests and measurements.
+        cta_frames.clear();
+        {
+            const char *m = getenv("B200Z_EXEC_MODE");
+            const bool force_warp = m && !strcmp(m, "warp"), force_cta = m && !strcmp(m, "cta");
+            for (size_t f = 0; f < frames.size() && !force_warp; f++) {
+                const FrameDesc &fd = frames[f];
+                if (fd.dict || fd.nblocks == 0) continue;
+                uint64_t src = 0;
+                for (uint32_t k = 0; k < fd.nblocks; k++) src += descs[fd.first_block + k].src_size;
+                if (force_cta || src >= 2048) cta_frames.push_back((uint32_t)f);
+            }
+        }
+        if ((e = d_sched.ensure(16 + 4 * (frames.size() + cta_frames.size()) + 16))) return e;
         HufSlot *hs = d_huf.as<HufSlot>();
         FseSlot *fs = d_fse.as<FseSlot>();
         const FseSlot *pd = c->d_predef;
@@ -291,6 +308,8 @@ struct Submission {
         if (!descs.empty()) CU(c, cudaMemcpyAsync(d_descs.p, descs.data(), descs.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice, stream));
         if (!frames.empty()) CU(c, cudaMemcpyAsync(d_frames.p, frames.data(), frames.size() * sizeof(FrameDesc), cudaMemcpyHostToDevice, stream));
         if (!states.empty()) CU(c, cudaMemcpyAsync(d_states.p, states.data(), states.size() * sizeof(FrameState), cudaMemcpyHostToDevice, stream));
+        if (!cta_frames.empty())
+            CU(c, cudaMemcpyAsync(d_sched.as<uint8_t>() + 16 + 4 * frames.size(), cta_frames.data(), 4 * cta_frames.size(), cudaMemcpyHostToDevice, stream));
         return 0;
     }
     PipelineArgs args(const uint8_t *d_input, uint8_t *d_output, uint64_t out_cap) const {
@@ -298,6 +317,9 @@ struct Submission {
         a.descs = d_descs.as<BlockDesc>(); a.aux = d_aux.as<BlockAux>(); a.frames = d_frames.as<FrameDesc>(); a.states = d_states.as<FrameState>();
         a.input = d_input; a.lit_scratch = d_lit.as<uint8_t>(); a.seq_scratch = d_seq.as<uint32_t>();
         a.output = d_output; a.output_cap = out_cap; a.nblocks = (uint32_t)descs.size(); a.nframes = (uint32_t)frames.size();
+        uint8_t *sp = d_sched.as<uint8_t>();
+        a.ticket = (uint32_t *)sp; a.resume = (uint32_t *)(sp + 16); a.cta_frames = (const uint32_t *)(sp + 16 + 4 * frames.size());
+        a.n_cta_frames = (uint32_t)cta_frames.size(); a.sched_bytes = (uint32_t)(16 + 4 * frames.size());
         return a;
     }
 };
@@ -391,7 +413,6 @@ static int plan_batch(b200z_batch *b, const uint8_t *in, size_t in_len, const b2
         st.hist[0] = dict ? dict->hist[0] : 1; st.hist[1] = dict ? dict->hist[1] : 4; st.hist[2] = dict ? dict->hist[2] : 8;
         TableCursor cur;
         if (dict_idx >= 0) cursor_from_carry(cur, s.carries[dict_idx], (uint32_t)dict_idx);
-        cur.hist_known = true; cur.hist[0] = st.hist[0]; cur.hist[1] = st.hist[1]; cur.hist[2] = st.hist[2];
         fi.first_block_end = b->block_end_bytes.size();
 
         uint64_t pos = consumed, bytes_read = consumed;
@@ -499,6 +520,7 @@ extern "C" int b200z_batch_run_profile(b200z_batch *b, uint8_t *d_output, size_t
     PipelineArgs a = s.args(b->d_input, d_output, output_cap);
     cudaEvent_t ev[kNumStages + 1];
     for (auto &e : ev) CU(c, cudaEventCreate(&e));
+    if (a.nframes) CU(c, cudaMemsetAsync(a.ticket, 0, a.sched_bytes, c->stream));
     CU(c, cudaEventRecord(ev[0], c->stream));
     for (int st = 0; st < kNumStages; st++) {
         int e = launch_stage(a, st, c->stream);
@@ -512,8 +534,9 @@ extern "C" int b200z_batch_run_profile(b200z_batch *b, uint8_t *d_output, size_t
     b->ran = true;
     return 0;
 }
-// One overlapped pass (as b200z_batch_run launches it) with an event after every kernel on its own stream:
-// out_ms[0..3] = completion time of k_setup, k_huf, k_fse, k_exec relative to the start of the pass.
+// One pass as b200z_batch_run launches it (k_huf on the side stream beside k_fse), with events on the main stream:
+// out_ms[0..3] = completion time, relative to the start of the pass, of k_setup, of the entropy pair (k_huf || k_fse),
+// of k_exec_cta and of k_exec.
 extern "C" int b200z_batch_run_timeline(b200z_batch *b, uint8_t *d_output, size_t output_cap, float *out_ms, size_t n) {
     if (!b || !out_ms || n < 4) return B200Z_ERR_INVALID_ARGUMENT;
     b200z_ctx *c = b->ctx;
@@ -522,25 +545,30 @@ extern "C" int b200z_batch_run_timeline(b200z_batch *b, uint8_t *d_output, size_
     if (!s.states.empty())
         CU(c, cudaMemcpyAsync(s.d_states.p, b->d_states_init.p, s.states.size() * sizeof(FrameState), cudaMemcpyDeviceToDevice, c->stream));
     PipelineArgs a = s.args(b->d_input, d_output, output_cap);
-    cudaEvent_t ev[4];
+    if (a.nframes) CU(c, cudaMemsetAsync(a.ticket, 0, a.sched_bytes, c->stream));
+    cudaEvent_t ev[5];
     for (auto &e : ev) CU(c, cudaEventCreate(&e));
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaEventRecord(ev[0], c->stream));
     int le = launch_stage(a, 0, c->stream);
     CU(c, cudaEventRecord(ev[1], c->stream));
-    if (!le) le = launch_stage(a, 1, c->stream);
+    if (!le && a.nblocks) {
+        CU(c, cudaEventRecord(c->ev_fork, c->stream));
+        CU(c, cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+        le = launch_stage(a, 2, c->stream);
+        if (!le) le = launch_stage(a, 1, c->side);
+        CU(c, cudaEventRecord(c->ev_join, c->side));
+        CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    }
     CU(c, cudaEventRecord(ev[2], c->stream));
-    // k_fse + k_exec exactly as b200z_batch_run launches them (k_exec as a programmatic dependent of k_fse: an event between
-    // the two would serialise them, so k_fse's own completion time is not observable here)
-    if (!le) le = launch_fse_exec(a, c->stream);
+    if (!le) le = launch_stage(a, 3, c->stream);
     CU(c, cudaEventRecord(ev[3], c->stream));
+    if (!le) le = launch_stage(a, 4, c->stream);
+    CU(c, cudaEventRecord(ev[4], c->stream));
     if (le) return c->set_cuda_err((cudaError_t)le, "launch_stage");
     c->launches += pipeline_launch_count(a);
     CU(c, cudaStreamSynchronize(c->stream));
-    CU(c, cudaEventElapsedTime(&out_ms[0], ev[0], ev[1]));
-    CU(c, cudaEventElapsedTime(&out_ms[1], ev[0], ev[2]));
-    out_ms[2] = -1.0f;
-    CU(c, cudaEventElapsedTime(&out_ms[3], ev[0], ev[3]));
+    for (int i = 0; i < 4; i++) CU(c, cudaEventElapsedTime(&out_ms[i], ev[0], ev[i + 1]));
     for (auto &e : ev) cudaEventDestroy(e);
     return 0;
 }
@@ -618,7 +646,25 @@ extern "C" int b200z_batch_debug_sequences(b200z_batch *b, uint32_t block, uint3
     if (cap_seqs < d.nseq) return B200Z_ERR_TARGET_TOO_SMALL;
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaMemcpy(host_out, b->sub.d_seq.as<uint32_t>() + d.seq_buf_off * 3, (size_t)d.nseq * 12, cudaMemcpyDeviceToHost));
+    // the device holds prefix sums {out_end, lit_end, of}: hand out {ll, ml, of} (of: see b200z_batch_debug_block_flags)
+    uint32_t p_out = 0, p_lit = 0;
+    for (size_t i = 0; i < d.nseq; i++) {
+        uint32_t *r = host_out + 3 * i;
+        const uint32_t oe = r[0], le = r[1], ll = le - p_lit, ml = oe - p_out - ll;
+        r[0] = ll; r[1] = ml; p_out = oe; p_lit = le;
+    }
     *nseq = d.nseq;
+    return 0;
+}
+// flags of a block's sequence stage: bit 0 = `of` values are raw offset_values (otherwise offsets after do_offset_history,
+// symbolic where they depend on the history at the block's start: tag << 30 | decrements, tag 1..3 = history slot + 1)
+extern "C" int b200z_batch_debug_block_flags(b200z_batch *b, uint32_t block, uint32_t *flags) {
+    if (!b || block >= b->sub.descs.size() || !flags) return B200Z_ERR_INVALID_ARGUMENT;
+    b200z_ctx *c = b->ctx;
+    CU(c, cudaStreamSynchronize(c->stream));
+    BlockAux ax;
+    CU(c, cudaMemcpy(&ax, b->sub.d_aux.as<BlockAux>() + block, sizeof ax, cudaMemcpyDeviceToHost));
+    *flags = ax.flags;
     return 0;
 }
 extern "C" void b200z_batch_destroy(b200z_batch *b) {
@@ -1045,7 +1091,10 @@ static int fd_submit(b200z_frame_decoder *d, const TableCursor &cur, uint32_t *f
     CU(c, cudaMemcpyAsync(aux.data(), s.d_aux.p, aux.size() * sizeof(BlockAux), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     uint64_t extra = 0;
-    for (auto &x : aux) extra += x.out_size;
+    for (size_t i = 0; i < aux.size(); i++) {   // blocks after the first failing one are never executed (nor looked at by the reference)
+        if (s.descs[i].host_status || aux[i].status || aux[i].pad) break;
+        extra += aux[i].out_size;
+    }
     if ((e = fd_reserve_out(d, extra))) return e;
     // stage B: execution into the persistent window buffer (frame byte 0 sits at d_out - base)
     s.frames[0].out_cap = d->base + d->d_out.cap;
@@ -1112,7 +1161,6 @@ static int fd_decode_blocks_impl(b200z_frame_decoder *d, b200z_read_fn rd, void 
         d->staging.clear();
         TableCursor cur;
         cursor_from_carry(cur, d->carry, 0);
-        cur.hist_known = true; cur.hist[0] = d->state.hist[0]; cur.hist[1] = d->state.hist[1]; cur.hist[2] = d->state.hist[2];
         std::vector<uint64_t> bytes_after;  // bytes_read_counter after each gathered block
         int pending_err = 0, pending_stage = 0;
         bool saw_last = false;

@@ -6,7 +6,11 @@
 //   HufSlot    : GPU-resident huff0 LUT (ruzstd huff0::HuffmanTable.decode, huff0_decoder.rs:57-74)
 //   FseTab     : GPU-resident FSE LUT (ruzstd fse::FSETable.decode, fse_decoder.rs:59-83), one per LL/OF/ML
 //   literals   : scratch, regenerated literals of every Compressed/Treeless literals section
-//   sequences  : scratch, 3 x u32 {ll, ml, of} per sequence (ruzstd blocks::sequence_section::Sequence)
+//   sequences  : scratch, 3 x u32 per sequence (ruzstd blocks::sequence_section::Sequence {ll, ml, of}) in PREFIX form:
+//                {out_end, lit_end, of}: out_end = sum of (ll + ml), lit_end = sum of ll over the block's sequences up to and
+//                including this one (mod 2^32), of = the offset after do_offset_history, symbolic when it depends on the
+//                repeat-offset history at the block's start (seq_sym_* below); or the raw offset_value when the block is
+//                flagged AUX_RAW_OFFSETS
 //   output     : plaintext, each frame at the caller's out_off
 #pragma once
 #include <stdint.h>
@@ -22,7 +26,26 @@ enum : uint32_t { MODE_PREDEFINED = 0, MODE_RLE = 1, MODE_FSE = 2, MODE_REPEAT =
 constexpr uint32_t HUF_MAX_BITS = 11;         // huff0_decoder.rs:9
 constexpr uint32_t HUF_TABLE_ENTRIES = 2048;  // 1 << 11
 constexpr uint32_t FSE_MAX_ENTRIES = 512;
-constexpr uint32_t FSE_PROGRESS_FINAL = 0xFFFFFFFFu;     // LL/ML max log 9 (sequence_section_decoder.rs:288-292)
+
+// ---- symbolic offsets.  k_fse decodes every block independently, so the repeat-offset history at a block's start
+// (scratch.rs:22,44; carried from the previous block of the frame) is unknown to it: do_offset_history
+// (sequence_execution.rs:59-118) runs on SYMBOLS.  A 32-bit value is either a concrete offset (< 2^30) or
+//   tag << 30 | d   (tag 1..3): "history slot (tag - 1) at the start of this block, minus d, saturating at 0"
+// (the only arithmetic the reference does on a history value is the saturating `- 1` of sequence_execution.rs:74).
+// The execution kernels resolve symbols with the frame's actual history in O(1) per sequence, in parallel.
+// A block that contains an offset code >= 30 (concrete values would collide with the tags) is decoded by the exact
+// path, which emits raw offset_values and flags the block AUX_RAW_OFFSETS.
+constexpr uint32_t SEQ_SYM_SHIFT = 30;
+constexpr uint32_t SEQ_SYM_DMASK = (1u << SEQ_SYM_SHIFT) - 1u;
+__host__ __device__ inline uint32_t seq_sym_resolve(uint32_t v, uint32_t h0, uint32_t h1, uint32_t h2) {
+    const uint32_t tag = v >> SEQ_SYM_SHIFT;
+    if (tag == 0) return v;
+    const uint32_t h = tag == 1 ? h0 : (tag == 2 ? h1 : h2), d = v & SEQ_SYM_DMASK;
+    return h > d ? h - d : 0u;
+}
+// BlockAux.flags
+constexpr uint32_t AUX_RAW_OFFSETS = 1u;   // `of` holds raw offset_values (exact path of k_fse); hist_after is not valid
+constexpr uint32_t AUX_WIDE = 2u;          // a prefix sum reached 2^31: positions are only meaningful as differences
 
 // huff0 LUT, split so that it costs 3 KiB of shared memory per block instead of 4 (occupancy: every block of a
 // 1 GiB submission is in flight at once): sym[i] = symbol, nb4[i >> 1] holds the 4-bit code length of entries
@@ -83,10 +106,7 @@ struct alignas(16) BlockDesc {
     uint32_t host_status;    // error the planner found for this block (stage in bits 16..23), 0 = none
     uint32_t block_in_frame; // ordinal of the block inside its frame
     uint32_t last;           // last block of the frame
-    uint32_t fse_resolves;   // 1: the repeat-offset history at this block's start is known at plan time (first block with
-                             // sequences of its frame), so k_fse resolves offsets itself (do_offset_history) from init_hist
-    uint32_t init_hist[3];
-    uint32_t pad1;
+    uint32_t pad0[5];
     const HufSlot *huf;      // table the literals decode with (own slot when lit_type == LT_COMPRESSED)
     HufSlot *huf_build;      // where a new Huffman table is built, or null
     const FseTab *ll, *of, *ml;  // tables the sequences decode with (null = uninitialised)
@@ -99,11 +119,10 @@ struct alignas(16) BlockAux {
     uint32_t out_size;       // decompressed size of the block (known after sequence decode)
     uint32_t lit_streams_off;// offset inside the block content where the jump table / single stream starts
     uint32_t seq_bits_off;   // offset inside the block content where the sequence bitstream starts
-    uint32_t sum_ll;         // sum of literal lengths over the block's sequences
+    uint32_t sum_ll;         // sum of literal lengths over the block's sequences (mod 2^32)
     uint32_t pad;            // sequence-stage status (code | stage << 16); literals-stage status is `status`
-    uint32_t hist_after[3];  // offset history after the block, when fse_resolves
-    uint32_t progress;       // sequences k_fse has published so far (FSE_PROGRESS_FINAL when the block's sequence stage is over);
-                             // k_exec runs beside k_fse and consumes sequences as they appear
+    uint32_t hist_after[3];  // offset history after the block (symbolic, seq_sym_*), unless AUX_RAW_OFFSETS
+    uint32_t flags;          // AUX_*
     uint32_t pad2[2];
 };
 

@@ -1,0 +1,442 @@
+// exec_cta.cuh -- k_exec_cta: LZ77 execution with the block's output assembled in SHARED MEMORY (included by kernels.cu).
+//
+// Replaces execute_sequences + do_offset_history (sequence_execution.rs:5-118) and DecodeBuffer::{push, repeat,
+// repeat_in_chunks} (decode_buffer.rs:74-141) for the common case; anything else (dictionary reach, invalid offsets,
+// blocks larger than the window buffer, error statuses, raw-offset blocks) is left to the warp-per-frame kernel
+// k_exec, which resumes the frame at the block where this kernel stopped (`resume[]`).
+//
+// One persistent CTA per SM takes frames from a ticket counter and walks a frame's blocks in order (the window /
+// offset-history chain of frame_decoder.rs:321-374 stays inside one CTA).  Per Compressed block:
+//   * the regenerated literals are staged into shared memory by ONE bulk copy (cp.async.bulk + mbarrier, TMA);
+//   * the block's output (<= 128 KiB) is assembled in shared memory, so every match source inside the block is a
+//     shared-memory read (no DRAM burst per match, which was 6.6 GB per GiB of output in round 1); sources in earlier
+//     blocks of the frame come from global memory (L2);
+//   * finished pieces leave as bulk stores shared -> global (cp.async.bulk, 16-byte aligned: the window is laid out
+//     at (global address & 15) so that shared and global alignment agree), overlapped with the rest of the block.
+// Work decomposition: sequences arrive in PREFIX form from k_fse ({out_end, lit_end, offset}), so any thread can place
+// any sequence without a scan.  A batch = 512 sequences, one per thread: the thread resolves its symbolic offset,
+// validates it, and publishes (a) an 8-byte record {match start, literal delta, offset} into a ring, (b) a bit at the
+// sequence's last byte in a block-wide bitmask, (c) for every 64-byte chunk whose first byte it owns, its index.
+// Output is then produced in ROWS of 128 bytes, one warp per row, FOUR bytes per lane: owner of the lane's first byte =
+// first64[chunk] + popc(mask bits below); a 4-byte word spans at most two sequences (match length >= 3), so two
+// records are fetched; each byte selects literal or match source and is read from shared memory; one aligned 32-bit
+// store per lane.  Rows whose sources lie in rows that are still in flight wait on a "rows done" bitmap (sources
+// always precede destinations, so the lowest unfinished row can always complete); sources inside the same row are
+// resolved inside the warp.  Overlapping matches use source = start + (k mod offset), the byte-order-preserving form
+// of repeat_in_chunks (decode_buffer.rs:113-141).
+#pragma once
+
+namespace b200z {
+
+constexpr uint32_t XC_WARPS = 16, XC_THREADS = XC_WARPS * 32;
+constexpr uint32_t XC_BATCH = XC_THREADS;                  // sequences per batch, one per thread
+constexpr uint32_t XC_RING = 2048;                         // record ring, 8-byte entries (4 batches)
+constexpr uint32_t XC_WIN_MAX = 128u << 10;                // largest block output handled here
+constexpr uint32_t XC_ROWS_MAX = XC_WIN_MAX / 128 + 1;     // + 1: the window starts at (global address & 15)
+constexpr uint32_t XC_DATA_BYTES = 184u << 10;             // window rows + staged literals
+constexpr uint32_t XC_MASK_BYTES = 16448;                  // >= XC_ROWS_MAX * 16, multiple of 64: one bit per window byte
+constexpr uint32_t XC_FIRST_BYTES = 8256;                  // >= XC_ROWS_MAX * 8: one u32 per 64 window bytes
+constexpr uint32_t XC_DONE_WORDS = 36;                     // >= XC_ROWS_MAX / 32 + 1 (+ slack for the frontier scan)
+constexpr uint32_t XC_OFF_MASK = XC_DATA_BYTES;
+constexpr uint32_t XC_OFF_FIRST = XC_OFF_MASK + XC_MASK_BYTES;
+constexpr uint32_t XC_OFF_RING = XC_OFF_FIRST + XC_FIRST_BYTES;
+constexpr uint32_t XC_OFF_DONE = XC_OFF_RING + XC_RING * 8;
+constexpr uint32_t XC_OFF_MISC = XC_OFF_DONE + XC_DONE_WORDS * 4;
+constexpr uint32_t XC_SMEM_BYTES = XC_OFF_MISC + 128;
+static_assert(XC_SMEM_BYTES <= 232448, "k_exec_cta: more than 227 KiB of shared memory");
+static_assert(XC_MASK_BYTES >= XC_ROWS_MAX * 16 && XC_FIRST_BYTES >= XC_ROWS_MAX * 8 && XC_DONE_WORDS * 32 >= XC_ROWS_MAX + 64, "k_exec_cta tables");
+constexpr uint32_t XC_SPIN_LIMIT = 1u << 18;               // bounded waits: a stuck wait turns into a bail-out, never a hang
+
+struct XcMisc {               // at XC_OFF_MISC
+    unsigned long long mbar;  // literals bulk-copy barrier
+    uint32_t ticket;
+    uint32_t bail;            // a thread found something this kernel does not handle (or a wait timed out)
+    uint32_t ovl[4];          // per batch (mod 4): some match overlaps its own output
+    uint32_t end_a[2];        // per batch (mod 2): window position where the batch's last sequence ends
+};
+
+// ---- PTX wrappers: mbarrier + bulk async copies (TMA, non-tensor form)
+__device__ __forceinline__ void xc_mbar_init(uint32_t a, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory"); }
+__device__ __forceinline__ void xc_mbar_expect_tx(uint32_t a, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory"); }
+__device__ __forceinline__ bool xc_mbar_try_wait(uint32_t a, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void xc_bulk_g2s(uint32_t sdst, const void *gsrc, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void xc_bulk_s2g(void *gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void xc_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void xc_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void xc_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void xc_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t xc_ld_acquire_shared(uint32_t a) { uint32_t v; asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t xc_ldg_cg_u8(const uint8_t *p) { uint32_t v; asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+// 8-byte ring record: lo = match start (window position, 18 bits) | literal delta << 18 (low 14 bits),
+//                     hi = literal delta >> 14 (4 bits) | offset << 4 (28 bits)
+// literal byte at window position a comes from shared-memory offset a + delta; match byte from a - offset.
+__device__ __forceinline__ uint2 xc_pack(uint32_t mstart_a, uint32_t lz, uint32_t off) { return make_uint2(mstart_a | (lz << 18), (lz >> 14) | (off << 4)); }
+struct XcRec { uint32_t x, lz, noff; };
+__device__ __forceinline__ XcRec xc_unpack(uint2 r) {
+    XcRec o;
+    o.x = r.x & 0x3FFFFu;
+    o.lz = __funnelshift_r(r.x, r.y, 18) & 0x3FFFFu;
+    o.noff = 0u - (r.y >> 4);
+    return o;
+}
+
+// Uniform (per block) values every thread holds
+struct XcBlk {
+    uint32_t S;          // shared-memory byte address of the data area
+    uint32_t woff;       // window position of the block's first byte (= its global address & 15)
+    uint32_t a_end;      // woff + out_size
+    uint32_t nrows;
+    uint32_t lit_s;      // shared-memory offset (from S) of literal 0
+    uint32_t nseq, ntot; // real sequences; + the trailing-literals pseudo sequence (sentinel record at index ntot)
+    uint32_t out_size, regen;
+    uint32_t h0, h1, h2; // offset history at the block's start
+    uint64_t reach;      // bytes of earlier output of the frame a match may reach back into (produced - drained)
+    const uint32_t *seqs;
+    uint8_t *gout;       // global address of the block's first output byte
+};
+
+// number of leading finished rows (>= F: the cached value is a valid lower bound)
+__device__ __forceinline__ uint32_t xc_frontier(uint32_t S_done, uint32_t F, uint32_t lane) {
+    const uint32_t w0 = F >> 5;
+    const uint32_t idx = w0 + lane;
+    const uint32_t word = idx < XC_DONE_WORDS ? xc_ld_acquire_shared(S_done + (idx << 2)) : 0u;
+    const uint32_t nf = __ballot_sync(0xffffffffu, word != 0xFFFFFFFFu);
+    if (nf == 0) return (w0 + 32u) << 5;
+    const uint32_t first = (uint32_t)__ffs((int)nf) - 1u;
+    const uint32_t wv = __shfl_sync(0xffffffffu, word, first);
+    return ((w0 + first) << 5) + ((uint32_t)__ffs((int)~wv) - 1u);
+}
+
+// One row of 128 window bytes by one warp.  Returns false if a wait timed out.
+template <bool FAR>
+__device__ __forceinline__ bool xc_row(const XcBlk &B, uint32_t r, uint32_t &F, bool has_ovl, uint32_t lane) {
+    const uint32_t S = B.S, S_mask = S + XC_OFF_MASK, S_first = S + XC_OFF_FIRST, S_ring = S + XC_OFF_RING, S_done = S + XC_OFF_DONE;
+    const uint32_t row_a = r << 7;
+    const uint32_t a0 = row_a + (lane << 2);
+    // ---- who owns my four bytes
+    const uint32_t c = a0 >> 6;
+    const uint2 M = lds64(S_mask + (c << 3));
+    const bool hi_half = (a0 & 32u) != 0;
+    const uint32_t W = hi_half ? M.y : M.x;
+    const uint32_t sh = a0 & 31u;
+    const uint32_t owner0 = lds32(S_first + (c << 2)) + (uint32_t)__popc(W & ((1u << sh) - 1u)) + (hi_half ? (uint32_t)__popc(M.x) : 0u);
+    const uint32_t nib = (W >> sh) & 7u;   // sequence ends at my bytes 0..2: the following bytes belong to the next sequence
+    const XcRec A = xc_unpack(lds64(S_ring + ((owner0 & (XC_RING - 1u)) << 3)));
+    const XcRec Bn = xc_unpack(lds64(S_ring + (((owner0 + 1u) & (XC_RING - 1u)) << 3)));
+    int32_t src[4];
+    bool mt[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const bool useB = k > 0 && (nib & ((1u << k) - 1u)) != 0u;
+        const uint32_t x = useB ? Bn.x : A.x, lz = useB ? Bn.lz : A.lz, noff = useB ? Bn.noff : A.noff;
+        const uint32_t a = a0 + (uint32_t)k;
+        mt[k] = a >= x;
+        src[k] = (int32_t)(a + (mt[k] ? noff : lz));
+        if (has_ovl) {   // overlapping match: byte kk comes from kk mod offset (warp-uniform branch, rare)
+            const uint32_t kk = a - x, off = 0u - noff;
+            if (mt[k] && kk >= off) src[k] = (int32_t)(x - off + kk % off);
+        }
+    }
+    // ---- sources in rows that are still in flight: wait until the frontier has passed them
+    const int32_t row_s = (int32_t)row_a;
+    {
+        int32_t need = -1;   // highest source position outside this row
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (mt[k] && src[k] < row_s) need = max(need, src[k]);
+        uint32_t spins = 0;
+        while (__any_sync(0xffffffffu, need >= (int32_t)(F << 7))) {
+            if (spins) __nanosleep(40);
+            F = xc_frontier(S_done, F, lane);
+            if (++spins > XC_SPIN_LIMIT) return false;
+        }
+    }
+    // ---- gather
+    uint32_t word = 0, pend = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const bool inrow = mt[k] && src[k] >= row_s;
+        uint32_t v = 0;
+        if (FAR) {
+            const bool far = mt[k] && src[k] < (int32_t)B.woff;
+            if (far) v = xc_ldg_cg_u8(B.gout + (src[k] - (int32_t)B.woff));
+            else if (!inrow) v = lds8(S + (uint32_t)src[k]);
+        } else if (!inrow) v = lds8(S + (uint32_t)src[k]);
+        word |= v << (8 * k);
+        pend |= inrow ? (1u << k) : 0u;
+    }
+    if (!__any_sync(0xffffffffu, pend != 0u)) {
+        sts32(S + a0, word);
+    } else {
+        // bytes whose source lies in this very row: the lowest pending byte's source is never pending, so every round
+        // completes at least one byte; typical depth 1-2
+        sts32(S + a0, word);
+        uint32_t spins = 0;
+        for (;;) {
+            __syncwarp();
+            const uint32_t pm0 = __ballot_sync(0xffffffffu, pend & 1u), pm1 = __ballot_sync(0xffffffffu, pend & 2u),
+                           pm2 = __ballot_sync(0xffffffffu, pend & 4u), pm3 = __ballot_sync(0xffffffffu, pend & 8u);
+            if ((pm0 | pm1 | pm2 | pm3) == 0u) break;
+            bool changed = false;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (pend & (1u << k)) {
+                    const uint32_t rel = (uint32_t)(src[k] - row_s);
+                    const uint32_t sb = rel & 3u, sl = rel >> 2;
+                    const uint32_t pm = sb == 0 ? pm0 : (sb == 1 ? pm1 : (sb == 2 ? pm2 : pm3));
+                    if (!((pm >> sl) & 1u)) {
+                        const uint32_t v = lds8(S + (uint32_t)src[k]);
+                        word = (word & ~(0xFFu << (8 * k))) | (v << (8 * k));
+                        pend &= ~(1u << k);
+                        changed = true;
+                    }
+                }
+            }
+            if (changed) sts32(S + a0, word);
+            if (++spins > 4096u) return false;
+        }
+    }
+    // ---- publish the row
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();
+        red_or_shared(S_done + ((r >> 5) << 2), 1u << (r & 31u));
+    }
+    return true;
+}
+
+// registers a thread carries from the record loads of a batch to its build step
+struct XcLoad { uint32_t cur_out, cur_lit, of, p_out, p_lit; };
+
+__device__ __forceinline__ XcLoad xc_load(const XcBlk &B, uint32_t k, uint32_t tid, uint32_t lane) {
+    XcLoad L;
+    const uint32_t i = k * XC_BATCH + tid;
+    L.cur_out = 0; L.cur_lit = 0; L.of = 0;
+    if (i < B.nseq) { const uint32_t *p = B.seqs + (uint64_t)i * 3; L.cur_out = p[0]; L.cur_lit = p[1]; L.of = p[2]; }
+    else if (i < B.ntot) { L.cur_out = B.out_size; L.cur_lit = B.regen; }   // trailing literals (sequence_execution.rs:40-44)
+    L.p_out = __shfl_up_sync(0xffffffffu, L.cur_out, 1); L.p_lit = __shfl_up_sync(0xffffffffu, L.cur_lit, 1);
+    if (lane == 0) {
+        if (i == 0 || i > B.nseq) { L.p_out = 0; L.p_lit = 0; }   // (i > nseq: the sentinel, which has no predecessor to look at)
+        else { const uint32_t *p = B.seqs + (uint64_t)(i - 1) * 3; L.p_out = p[0]; L.p_lit = p[1]; }
+    }
+    return L;
+}
+
+// publishes sequence i = k * XC_BATCH + tid (record, end bit, chunk owners); validates what the rows rely on
+__device__ __forceinline__ void xc_build(const XcBlk &B, uint32_t k, uint32_t tid, const XcLoad &L, volatile XcMisc *misc) {
+    const uint32_t S = B.S, S_mask = S + XC_OFF_MASK, S_first = S + XC_OFF_FIRST, S_ring = S + XC_OFF_RING;
+    const uint32_t i = k * XC_BATCH + tid;
+    if (i > B.ntot) return;
+    if (i == B.ntot) {
+        // sentinel: bytes of the last row beyond the block copy themselves (never a match, literal delta 0)
+        const uint2 rec = xc_pack(0x3FFFFu, 0u, 1u);
+        sts64(S_ring + ((i & (XC_RING - 1u)) << 3), rec.x, rec.y);
+        for (uint32_t c = (B.a_end + 63u) >> 6; c < B.nrows * 2u; c++) sts32(S_first + (c << 2), i);
+        misc->end_a[k & 1u] = B.a_end;
+        return;
+    }
+    const bool real = i < B.nseq;
+    const uint32_t ll = L.cur_lit - L.p_lit, start = L.p_out, end = L.cur_out;
+    const uint32_t mstart = start + ll;
+    const uint32_t ml = end - mstart;
+    const uint32_t off = real ? seq_sym_resolve(L.of, B.h0, B.h1, B.h2) : 1u;
+    // everything the rows rely on: positions inside the block, literals inside the literal buffer, offsets inside the
+    // frame's earlier output.  (Zero offsets, dictionary reach, offsets beyond the buffer: the warp kernel reports
+    // ExecuteSequencesError / DecodeBufferError exactly as the reference does.)
+    bool bad = end > B.out_size || end <= start || mstart > end || L.cur_lit > B.regen || L.cur_lit < L.p_lit;
+    if (real) bad = bad || off == 0u || off >= (1u << 28) || (uint64_t)off > B.reach + mstart || ml < 3u;
+    if (bad) { misc->bail = 1u; return; }
+    if (off < ml) misc->ovl[k & 3u] = 1u;
+    const uint32_t start_a = B.woff + start, end_a = B.woff + end;
+    // literal j of the block sits at shared offset lit_s + j; literal byte at window position a is literal number
+    // (a - woff) - (match bytes before this sequence) = a - woff - (mstart - cur_lit)
+    const uint32_t lz = B.lit_s + L.cur_lit - B.woff - mstart;
+    const uint2 rec = xc_pack(B.woff + mstart, lz, off);
+    sts64(S_ring + ((i & (XC_RING - 1u)) << 3), rec.x, rec.y);
+    red_or_shared(S_mask + (((end_a - 1u) >> 5) << 2), 1u << ((end_a - 1u) & 31u));
+    const uint32_t c_lo = i == 0 ? 0u : (start_a + 63u) >> 6, c_hi = (end_a - 1u) >> 6;
+    for (uint32_t c = c_lo; c <= c_hi; c++) sts32(S_first + (c << 2), i);
+    if (i + 1 == (k + 1) * XC_BATCH) misc->end_a[k & 1u] = end_a;   // the batch's last sequence (a later batch exists: the sentinel)
+}
+
+__global__ void __launch_bounds__(XC_THREADS, 1) k_exec_cta(const BlockDesc *__restrict__ descs, const BlockAux *__restrict__ aux,
+                                                            const FrameDesc *__restrict__ frames, FrameState *__restrict__ states,
+                                                            const uint8_t *__restrict__ input, const uint8_t *__restrict__ lit_scratch,
+                                                            const uint32_t *__restrict__ seq_scratch, uint8_t *__restrict__ output, uint64_t output_cap,
+                                                            const uint32_t *__restrict__ cta_frames, uint32_t n_cta_frames,
+                                                            uint32_t *__restrict__ resume, uint32_t *__restrict__ ticket) {
+    extern __shared__ __align__(128) uint8_t xc_smem[];
+    const uint32_t S = (uint32_t)__cvta_generic_to_shared(xc_smem);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    volatile XcMisc *misc = reinterpret_cast<volatile XcMisc *>(xc_smem + XC_OFF_MISC);
+    const uint32_t S_mbar = S + XC_OFF_MISC;   // XcMisc::mbar is the first member
+    if (tid == 0) {
+        xc_mbar_init(S_mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t lit_parity = 0;
+
+    for (;;) {
+        if (tid == 0) misc->ticket = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t t = misc->ticket;
+        __syncthreads();
+        if (t >= n_cta_frames) break;
+        const uint32_t f = cta_frames[t];
+        const FrameDesc &fd = frames[f];
+        const FrameState fs = states[f];
+        uint32_t h0 = fs.hist[0], h1 = fs.hist[1], h2 = fs.hist[2];
+        uint64_t produced = fs.produced, counter = fs.counter;
+        const uint64_t drained = fs.drained;
+        uint64_t cap = fd.out_cap;
+        if (fd.out_off > output_cap) cap = 0; else if (cap > output_cap - fd.out_off) cap = output_cap - fd.out_off;
+        uint8_t *out = output + fd.out_off;
+        uint32_t blocks_done = fs.blocks_done;
+        const uint32_t nblocks = fd.nblocks;
+        bool bailed = fs.status != 0 || fd.dict != nullptr;
+        bool fresh = true;   // no block of this frame has been stored by this CTA yet
+        uint32_t bi = 0;
+        for (; bi < nblocks && !bailed; bi++) {
+            const uint32_t b = fd.first_block + bi;
+            const BlockDesc &d = descs[b];
+            const BlockAux &ax = aux[b];
+            if (d.host_status || ax.status) { bailed = true; break; }
+            const uint32_t btype = d.btype;
+            if (btype != BT_COMPRESSED) {
+                const uint32_t n = d.raw_size;
+                if (produced + n > cap) { bailed = true; break; }
+                uint8_t *dst = out + produced;
+                if (btype == BT_RAW) { const uint8_t *srcp = input + d.src_off; for (uint32_t j = tid; j < n; j += XC_THREADS) dst[j] = srcp[j]; }
+                else { const uint8_t v = input[d.src_off]; for (uint32_t j = tid; j < n; j += XC_THREADS) dst[j] = v; }
+                produced += n;   // extend_from_reader: total_output_counter untouched (decode_buffer.rs:66-72)
+                blocks_done++;
+                fresh = false;
+                __syncthreads();
+                continue;
+            }
+            const uint32_t nseq = d.nseq;
+            if (nseq && (ax.pad || (ax.flags & (AUX_RAW_OFFSETS | AUX_WIDE)))) { bailed = true; break; }
+            const uint32_t out_size = ax.out_size, regen = d.regen_size;
+            const uint32_t sum_ll = nseq ? ax.sum_ll : 0u;
+            if (out_size > XC_WIN_MAX || produced + out_size > cap || sum_ll > regen || regen > out_size) { bailed = true; break; }
+            if (out_size == 0) { blocks_done++; continue; }
+            XcBlk B;
+            B.S = S;
+            B.gout = out + produced;
+            B.woff = (uint32_t)((uintptr_t)B.gout & 15u);
+            B.a_end = B.woff + out_size;
+            const uint32_t wbytes = (B.a_end + 127u) & ~127u;
+            B.nrows = wbytes >> 7;
+            B.nseq = nseq; B.ntot = nseq + (regen > sum_ll ? 1u : 0u);
+            B.out_size = out_size; B.regen = regen;
+            B.h0 = h0; B.h1 = h1; B.h2 = h2;
+            B.reach = produced - drained;
+            B.seqs = seq_scratch + d.seq_buf_off * 3;
+            // ---- literals: where they come from, how they are staged
+            const uint32_t lt = d.lit_type;
+            const uint8_t *lit_g = nullptr;
+            uint32_t loff = 0;
+            if (lt == LT_RAW) { const uint8_t *p = input + d.src_off + d.lit_off; loff = (uint32_t)((uintptr_t)p & 15u); lit_g = p - loff; }
+            else if (lt != LT_RLE) lit_g = lit_scratch + d.lit_buf_off;
+            const uint32_t lit_bytes = (loff + regen + 15u) & ~15u;
+            if (wbytes + lit_bytes > XC_DATA_BYTES) { bailed = true; break; }
+            B.lit_s = wbytes + loff;
+            const bool has_far = B.reach != 0;
+            // ---- the window and the literal area are free once the previous block's bulk stores have read them; a block
+            // that may read earlier output of its frame also needs those stores to be complete in global memory
+            if (tid == 0) { if (has_far && !fresh) xc_bulk_wait0(); else xc_bulk_wait_read0(); }
+            for (uint32_t j = tid; j < XC_MASK_BYTES / 16; j += XC_THREADS) sts128(S + XC_OFF_MASK + (j << 4), 0u, 0u, 0u, 0u);
+            if (tid < XC_DONE_WORDS) sts32(S + XC_OFF_DONE + (tid << 2), 0u);
+            if (tid == 0) { misc->bail = 0; misc->ovl[0] = 0; misc->ovl[1] = 0; misc->ovl[2] = 0; misc->ovl[3] = 0; misc->end_a[0] = 0; misc->end_a[1] = 0; }
+            __syncthreads();
+            const bool tma_lit = lt != LT_RLE && regen != 0;
+            if (tma_lit) {
+                if (tid == 0) {
+                    xc_mbar_expect_tx(S_mbar, lit_bytes);
+                    for (uint32_t o = 0; o < lit_bytes; o += 32768u) xc_bulk_g2s(S + wbytes + o, lit_g + o, min(32768u, lit_bytes - o), S_mbar);
+                }
+            } else if (lt == LT_RLE) {
+                const uint32_t v = input[d.src_off + d.lit_off] * 0x01010101u;
+                for (uint32_t j = tid; j < lit_bytes / 16; j += XC_THREADS) sts128(S + wbytes + (j << 4), v, v, v, v);
+            }
+            const uint32_t nbatch = (B.ntot + 1u + XC_BATCH - 1u) / XC_BATCH;
+            {
+                const XcLoad L0 = xc_load(B, 0, tid, lane);
+                xc_build(B, 0, tid, L0, misc);
+            }
+            __syncthreads();
+            bool blk_bail = misc->bail != 0;
+            if (tma_lit) {   // also when bailing out: the copy must have landed before the barrier / the area are used again
+                uint32_t spins = 0;
+                while (!xc_mbar_try_wait(S_mbar, lit_parity)) { if (++spins > XC_SPIN_LIMIT) { misc->bail = 2u; break; } }
+                lit_parity ^= 1u;
+            }
+            uint32_t row_lo = 0, stored_a = (B.woff + 15u) & ~15u, F = 0;
+            for (uint32_t k = 0; k < nbatch && !blk_bail; k++) {
+                const bool last = k + 1 == nbatch;
+                XcLoad Ln;
+                if (!last) Ln = xc_load(B, k + 1, tid, lane);
+                const uint32_t row_hi = last ? B.nrows : (misc->end_a[k & 1u] >> 7);
+                const bool has_ovl = (misc->ovl[k & 3u] | misc->ovl[(k + 3u) & 3u]) != 0u;
+                if (tid == 0) misc->ovl[(k + 2u) & 3u] = 0u;
+                if (F < row_lo) F = row_lo;
+                bool ok = true;
+                for (uint32_t r = row_lo + warp; r < row_hi && ok; r += XC_WARPS)
+                    ok = has_far ? xc_row<true>(B, r, F, has_ovl, lane) : xc_row<false>(B, r, F, has_ovl, lane);
+                if (!ok && lane == 0) misc->bail = 2u;
+                if (!last) xc_build(B, k + 1, tid, Ln, misc);
+                xc_fence_proxy_async();
+                __syncthreads();
+                blk_bail = misc->bail != 0;
+                row_lo = row_hi;
+                // ---- rows below row_hi are final: send the aligned part to global memory while the next batch runs
+                uint32_t hi_a = min(row_hi << 7, B.a_end) & ~15u;
+                if (!blk_bail && hi_a > stored_a) {
+                    if (tid == 0) {
+                        for (uint32_t o = stored_a; o < hi_a; o += 32768u) xc_bulk_s2g(B.gout + (o - B.woff), S + o, min(32768u, hi_a - o));
+                        xc_bulk_commit();
+                    }
+                    stored_a = hi_a;
+                }
+            }
+            if (blk_bail) { bailed = true; break; }
+            // ---- head / tail bytes around the 16-byte aligned part
+            {
+                const uint32_t head_end = min((B.woff + 15u) & ~15u, B.a_end);
+                const uint32_t tail_beg = max((B.woff + 15u) & ~15u, B.a_end & ~15u);
+                if (tid < 16) { const uint32_t a = B.woff + tid; if (a < head_end) B.gout[a - B.woff] = (uint8_t)lds8(S + a); }
+                else if (tid < 32) { const uint32_t a = tail_beg + (tid - 16u); if (a < B.a_end) B.gout[a - B.woff] = (uint8_t)lds8(S + a); }
+            }
+            if (nseq) {   // the history after the block, in terms of the history at its start (k_fse, symbolic)
+                const uint32_t a0 = ax.hist_after[0], a1 = ax.hist_after[1], a2 = ax.hist_after[2];
+                const uint32_t n0 = seq_sym_resolve(a0, h0, h1, h2), n1 = seq_sym_resolve(a1, h0, h1, h2), n2 = seq_sym_resolve(a2, h0, h1, h2);
+                h0 = n0; h1 = n1; h2 = n2;
+            }
+            produced += out_size; counter += out_size;
+            blocks_done++;
+            fresh = false;
+            __syncthreads();   // head/tail reads of the window are done before the next block's prologue touches it
+        }
+        if (tid == 0) {
+            FrameState &o = states[f];
+            if (fs.status == 0) {
+                o.hist[0] = h0; o.hist[1] = h1; o.hist[2] = h2;
+                o.produced = produced; o.counter = counter; o.blocks_done = blocks_done;
+            }
+            // what is left for k_exec: the rest of the frame from block `bi`, or only the frame-level epilogue, or nothing
+            resume[f] = bailed ? bi : (fd.host_status ? nblocks : nblocks + 1u);
+        }
+    }
+    if (tid == 0) xc_bulk_wait0();
+}
+
+}  // namespace b200z

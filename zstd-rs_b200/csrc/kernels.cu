@@ -83,6 +83,9 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(const BlockDesc *__r
             if (d.huf == nullptr) st_lit = mk_status(B200Z_ERR_LIT_UNINITIALIZED_HUFFMAN_TABLE, B200Z_STAGE_LITERALS);
         }
         if (d.nseq != 0 && !d.host_status) {
+            // a table whose build fails (or is never reached) must read as uninitialised to every later user of the slot
+            if (lane == 0 && d.fse_build) { d.fse_build->ll.valid = 0; d.fse_build->ll.log = 0; d.fse_build->of.valid = 0; d.fse_build->of.log = 0; d.fse_build->ml.valid = 0; d.fse_build->ml.log = 0; }
+            __syncwarp();
             const uint8_t *p = content + d.seq_off;
             uint32_t rem = d.src_size - d.seq_off;
             int e = setup_seq_table_warp(sc, d.modes >> 6, p, rem, 9, 35, d.fse_build ? &d.fse_build->ll : nullptr, B200Z_ERR_SEQ_MISSING_BYTE_FOR_RLE_LL_TABLE);
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(const BlockDesc *__r
         BlockAux a;
         a.status = st_lit;   // literals-stage status; the sequence-stage status travels in `pad` until k_exec orders them
         a.out_size = 0; a.lit_streams_off = lit_streams_off; a.seq_bits_off = seq_bits_off; a.sum_ll = 0; a.pad = st_seq;
-        a.hist_after[0] = a.hist_after[1] = a.hist_after[2] = 0; a.progress = 0; a.pad2[0] = a.pad2[1] = 0;
+        a.hist_after[0] = a.hist_after[1] = a.hist_after[2] = 0; a.flags = 0; a.pad2[0] = a.pad2[1] = 0;
         aux[b] = a;
     }
 }
@@ -488,12 +491,6 @@ __device__ __forceinline__ uint32_t offset_history_step(uint32_t of, uint32_t ll
     return actual;
 }
 
-// progress hand-off to k_exec (which runs concurrently): records first, fence, then the counter
-__device__ __forceinline__ void fse_publish(BlockAux *aux, uint32_t b, uint32_t nseq_done) {
-    __threadfence();
-    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(&aux[b].progress), "r"(nseq_done) : "memory");
-}
-
 struct FseState {
     uint32_t e;   // current 16-bit entry
     __device__ __forceinline__ uint32_t sym() const { return e >> 10; }
@@ -514,24 +511,26 @@ struct FseChain {
     uint32_t b; const BlockDesc *d; bool active, run, bad; uint32_t st_seq;
     const FseTab *tl, *to, *tm;
     uint32_t logL, logM, logO, qTL, qTM, qTO;   // accuracy logs; shared-memory table addresses biased by -2^log entries
-    uint32_t *out; uint32_t nseq; bool resolve;
+    uint32_t *out; uint32_t nseq;
     // running
     PosRing br;
-    uint32_t eL, eM, eO, h0, h1, h2;
-    uint64_t sum_ml;
-    uint32_t flags, or_of, max_x, i;
+    uint32_t eL, eM, eO, h0, h1, h2;   // h*: repeat-offset history, symbolic (b200z_types.h seq_sym_*)
+    uint32_t out_end, lit_end, ovf;    // prefix sums of ll + ml and of ll; OR of all their values (bit 31 = reached 2^31)
+    uint32_t flags, max_of, max_x, i;
 };
 
 __device__ __forceinline__ uint32_t fse_lds16(uint32_t addr) { uint16_t w; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(w) : "r"(addr) : "memory"); return w; }
 
-// one sequence (sequence_section_decoder.rs:168-207); `update` = not the block's last sequence
+// one sequence (sequence_section_decoder.rs:168-207); `update` = not the block's last sequence.  The record written is
+// {out_end, lit_end, offset}: running sums of ll + ml and of ll (so that the execution kernels can place any sequence
+// without a scan) and the offset after do_offset_history on symbolic history values.
 __device__ __forceinline__ void fse_step(FseChain &c, uint32_t qLL, uint32_t qML, uint32_t &o_ll, uint32_t &o_ml, uint32_t &o_of, bool update) {
     uint32_t hi, lo;
     c.br.window(hi, lo);
     const uint32_t cL = c.eL >> 10, cM = c.eM >> 10, cO = c.eO >> 10;
     const uint32_t vL = lds32(qLL + (cL << 2)), vM = lds32(qML + (cM << 2));   // base | extra_bits << 24
     const uint32_t xL = vL >> 24, xM = vM >> 24, xO = cO;
-    c.or_of |= cO;          // offset code > 31 is checked per group (LL/ML codes are capped by table construction, scratch.rs:36-40)
+    c.max_of = max(c.max_of, cO);   // offset codes >= 30 are checked per group (LL/ML codes are capped by table construction, scratch.rs:36-40)
     // extra bits: OF, ML, LL (get_bits_triple, sequence_section_decoder.rs:185)
     const uint32_t xsum = xO + xM + xL;
     c.max_x = max(c.max_x, xsum);   // > 32 extra bits in one sequence: not for this path, checked per group
@@ -539,11 +538,12 @@ __device__ __forceinline__ void fse_step(FseChain &c, uint32_t qLL, uint32_t qML
     const uint32_t obits = shr_c(hi, 32u - xO), ml_add = shr_c(t1, 32u - xM), ll_add = shr_c(t2, 32u - xL);
     uint32_t offset = obits + (1u << (cO & 31u));
     const uint32_t ll = (vL & 0xFFFFFFu) + ll_add, ml = (vM & 0xFFFFFFu) + ml_add;
-    c.sum_ml += ml;
-    {   // do_offset_history (sequence_execution.rs:59-118), branch-free; the result is used only when `resolve`
+    c.lit_end += ll; c.out_end += ll + ml;
+    c.ovf |= c.out_end | c.lit_end;
+    {   // do_offset_history (sequence_execution.rs:59-118), branch-free, on symbolic history values
         const bool rep = offset <= 3u;
         const uint32_t r = offset - 1u + (ll == 0u ? 1u : 0u);   // 0..3 when rep
-        const uint32_t h0m1 = c.h0 - (c.h0 != 0u ? 1u : 0u);      // saturating_sub (:74)
+        const uint32_t h0m1 = (c.h0 >> SEQ_SYM_SHIFT) ? c.h0 + 1u : c.h0 - (c.h0 != 0u ? 1u : 0u);   // saturating_sub (:74); symbols count the decrements
         uint32_t cand = c.h0;
         cand = r == 1u ? c.h1 : cand;
         cand = r == 2u ? c.h2 : cand;
@@ -553,9 +553,9 @@ __device__ __forceinline__ void fse_step(FseChain &c, uint32_t qLL, uint32_t qML
         c.h2 = keep2 ? c.h2 : c.h1;
         c.h1 = keep1 ? c.h1 : c.h0;
         c.h0 = actual;
-        offset = c.resolve ? actual : offset;
+        offset = actual;
     }
-    o_ll = ll; o_ml = ml; o_of = offset;
+    o_ll = c.out_end; o_ml = c.lit_end; o_of = offset;
     if (update) {   // state updates LL, ML, OF (:198-207); compact entries (b200z_types.h): nb = log - floor(log2 f)
         const uint32_t fL = c.eL & 1023u, fM = c.eM & 1023u, fO = c.eO & 1023u;
         const uint32_t nbL = c.logL - bfind32(fL), nbM = c.logM - bfind32(fM), nbO = c.logO - bfind32(fO);
@@ -569,7 +569,7 @@ __device__ __forceinline__ void fse_step(FseChain &c, uint32_t qLL, uint32_t qML
     } else c.br.P -= (int32_t)xsum;
 }
 __device__ __forceinline__ void fse_group_end(FseChain &c, const uint32_t (&stage)[12]) {
-    c.flags |= (uint32_t)(c.br.P < 0) | (uint32_t)(c.max_x > 32u) | (c.or_of >> 5);   // bits_remaining only decreases: one check per group is equivalent
+    c.flags |= (uint32_t)(c.br.P < 0) | (uint32_t)(c.max_x > 32u) | ((c.max_of + 2u) >> 5);   // bits_remaining only decreases: one check per group is equivalent
     uint4 *o4 = reinterpret_cast<uint4 *>(c.out + 3 * c.i);
     o4[0] = make_uint4(stage[0], stage[1], stage[2], stage[3]);
     o4[1] = make_uint4(stage[4], stage[5], stage[6], stage[7]);
@@ -580,9 +580,11 @@ __device__ __forceinline__ void fse_group_end(FseChain &c, const uint32_t (&stag
 __device__ __noinline__ void fse_exact_block(const BlockDesc *d, BlockAux *aux, uint32_t b, const uint8_t *input, uint32_t *seq_scratch,
                                              const uint16_t *TL, const uint16_t *TM, const uint16_t *TO, const FseTab *tl, const FseTab *to, const FseTab *tm,
                                              const uint32_t *s_ll_base, const uint32_t *s_ml_base, const uint8_t *s_ll_bits, const uint8_t *s_ml_bits, uint32_t st_seq) {
+    // Emits the same prefix-form records as the fast path but with RAW offset_values (full 32-bit range: an offset code
+    // >= 30 cannot be told from a symbol) and flags the block AUX_RAW_OFFSETS: the warp-per-frame execution kernel then
+    // runs do_offset_history itself, sequence by sequence.
     uint32_t err = 0;
-    uint64_t sum_ml = 0, sum_ll = 0;
-    uint32_t h0r = 0, h1r = 0, h2r = 0;
+    uint32_t out_end = 0, lit_end = 0, ovf = 0;
     {
         const uint8_t *src = input + d->src_off + aux[b].seq_bits_off;
         uint32_t len = d->src_size - aux[b].seq_bits_off;
@@ -597,8 +599,6 @@ __device__ __noinline__ void fse_exact_block(const BlockDesc *d, BlockAux *aux, 
         uint32_t *out = seq_scratch + d->seq_buf_off * 3;   // 16-byte aligned: the planner rounds seq_buf_off to 4 sequences
         const uint32_t nseq = d->nseq;
         uint32_t stage[12];
-        const bool resolve = d->fse_resolves != 0;
-        uint32_t h0 = d->init_hist[0], h1 = d->init_hist[1], h2 = d->init_hist[2];
         // one sequence; `last` suppresses the state update exactly like `target.len() < num_sequences` (:198)
         auto one = [&](uint32_t &ll, uint32_t &ml, uint32_t &offset, bool last) {
             const uint32_t ll_code = sl.sym(), ml_code = sm.sym(), of_code = so.sym();
@@ -615,9 +615,9 @@ __device__ __noinline__ void fse_exact_block(const BlockDesc *d, BlockAux *aux, 
             uint32_t ml_add = ml_bits ? br.hi >> (32u - ml_bits) : 0u; br.skip(ml_bits);
             uint32_t ll_add = ll_bits ? br.hi >> (32u - ll_bits) : 0u; br.skip(ll_bits);
             offset = obits + (1u << of_code);
-            ll = s_ll_base[ll_code] + ll_add; ml = s_ml_base[ml_code] + ml_add;
-            sum_ll += ll; sum_ml += ml;
-            if (resolve) offset = offset_history_step(offset, ll, h0, h1, h2);   // `of` becomes the actual offset
+            const uint32_t llv = s_ll_base[ll_code] + ll_add, mlv = s_ml_base[ml_code] + ml_add;
+            lit_end += llv; out_end += llv + mlv; ovf |= out_end | lit_end;
+            ll = out_end; ml = lit_end;   // the record is {out_end, lit_end, raw offset}
             if (!last) {
                 br.refill();
                 uint32_t aL = nbL ? br.hi >> (32u - nbL) : 0u; br.skip(nbL);
@@ -645,19 +645,15 @@ __device__ __noinline__ void fse_exact_block(const BlockDesc *d, BlockAux *aux, 
         }
         if (!err && br.p > 0) err = B200Z_ERR_SEQ_EXTRA_BITS;
         if (err) st_seq = mk_status(err, B200Z_STAGE_SEQUENCES);
-        h0r = h0; h1r = h1; h2r = h2;
     }
     aux[b].pad = st_seq;
-    if (d->fse_resolves) { aux[b].hist_after[0] = h0r; aux[b].hist_after[1] = h1r; aux[b].hist_after[2] = h2r; }
-    aux[b].sum_ll = (uint32_t)(sum_ll > 0xffffffffull ? 0xffffffffull : sum_ll);
-    uint64_t total = sum_ml + d->regen_size;
-    aux[b].out_size = (uint32_t)(total > 0xffffffffull ? 0xffffffffull : total);
-    fse_publish(aux, b, FSE_PROGRESS_FINAL);
+    aux[b].sum_ll = lit_end;
+    aux[b].flags = AUX_RAW_OFFSETS | ((ovf >> 31) ? AUX_WIDE : 0u);
+    aux[b].out_size = (ovf >> 31) ? 0xffffffffu : out_end - lit_end + d->regen_size;   // sum of ml + regenerated literals
 }
 
 __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs, BlockAux *__restrict__ aux, const uint8_t *__restrict__ input,
                                           uint32_t *__restrict__ seq_scratch, uint32_t nblocks) {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // this CTA is resident: k_exec may follow (launch_pipeline_overlapped)
     extern __shared__ __align__(16) uint8_t smem_fse[];
     uint16_t *tabs = reinterpret_cast<uint16_t *>(smem_fse);
     uint32_t *s_ll_base = reinterpret_cast<uint32_t *>(smem_fse + FSE_BLOCKS_PER_CTA * FSE_TAB_U16 * 2);
@@ -725,9 +721,10 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
         const uint16_t *TL = tabs + slot * FSE_TAB_U16;
         const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(s_ring + slot * RING_STRIDE) + 16u;   // slot 0; the mirror slot sits below
         c.bad = !c.br.init(src, len, ring_addr) || !c.tl || !c.tl->valid || !c.to || !c.to->valid || !c.tm || !c.tm->valid;
-        c.flags = 0; c.or_of = 0; c.max_x = 0; c.i = 0; c.sum_ml = 0;
-        c.nseq = c.d->nseq; c.resolve = c.d->fse_resolves != 0;
-        c.h0 = c.d->init_hist[0]; c.h1 = c.d->init_hist[1]; c.h2 = c.d->init_hist[2];
+        if (!c.bad) c.bad = c.tl->log > 9u || c.tm->log > 9u || c.to->log > 8u;   // never true for a built table: the staged copies are sized for these
+        c.flags = 0; c.max_of = 0; c.max_x = 0; c.i = 0; c.out_end = 0; c.lit_end = 0; c.ovf = 0;
+        c.nseq = c.d->nseq;
+        c.h0 = 1u << SEQ_SYM_SHIFT; c.h1 = 2u << SEQ_SYM_SHIFT; c.h2 = 3u << SEQ_SYM_SHIFT;   // "slot k at the block's start"
         c.out = seq_scratch + c.d->seq_buf_off * 3;
         if (!c.bad) {
             c.logL = c.tl->log; c.logM = c.tm->log; c.logO = c.to->log;
@@ -765,11 +762,6 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
 #pragma unroll
                 for (int k = 0; k < (int)FSE_CHAINS; k++) { ch[k].i = i; fse_group_end(ch[k], stage[k]); anyflag |= ch[k].flags; }
                 if (anyflag) { i += 4; break; }
-                if (((i + 4) & 127u) == 0) {   // every 128 sequences: the fence costs ~1 us
-                    __threadfence();
-#pragma unroll
-                    for (int k = 0; k < (int)FSE_CHAINS; k++) asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(&aux[ch[k].b].progress), "r"(i + 4) : "memory");
-                }
             }
 #pragma unroll
             for (int k = 0; k < (int)FSE_CHAINS; k++) ch[k].i = i;
@@ -787,7 +779,6 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
                 for (int q = 0; q < 4; q++) { fse_step(c, qLL, qML, stage[3 * q], stage[3 * q + 1], stage[3 * q + 2], true); if (q & 1) c.br.service(); }
                 fse_group_end(c, stage);
                 if (c.flags) break;
-                if (((c.i + 4) & 127u) == 0) fse_publish(aux, c.b, c.i + 4);
             }
         }
         if (!c.flags) {
@@ -795,16 +786,17 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
                 uint32_t ll, ml, of;
                 fse_step(c, qLL, qML, ll, ml, of, c.i + 1 < c.nseq);
                 c.br.service();
-                c.flags |= (uint32_t)(c.br.P < 0) | (uint32_t)(c.max_x > 32u) | (c.or_of >> 5);
+                c.flags |= (uint32_t)(c.br.P < 0) | (uint32_t)(c.max_x > 32u) | ((c.max_of + 2u) >> 5);
                 c.out[3 * c.i] = ll; c.out[3 * c.i + 1] = ml; c.out[3 * c.i + 2] = of;
             }
         }
         c.bad = c.flags != 0 || c.br.P != 0;
         if (!c.bad) {
             aux[c.b].pad = 0;
-            if (c.resolve) { aux[c.b].hist_after[0] = c.h0; aux[c.b].hist_after[1] = c.h1; aux[c.b].hist_after[2] = c.h2; }
-            uint64_t total = c.sum_ml + c.d->regen_size;
-            aux[c.b].out_size = (uint32_t)(total > 0xffffffffull ? 0xffffffffull : total);
+            aux[c.b].hist_after[0] = c.h0; aux[c.b].hist_after[1] = c.h1; aux[c.b].hist_after[2] = c.h2;
+            aux[c.b].sum_ll = c.lit_end;
+            aux[c.b].flags = (c.ovf >> 31) ? AUX_WIDE : 0u;
+            aux[c.b].out_size = (c.ovf >> 31) ? 0xffffffffu : c.out_end - c.lit_end + c.d->regen_size;   // sum of ml + regenerated literals
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -813,8 +805,8 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
     for (int k = 0; k < (int)FSE_CHAINS; k++) {
         FseChain &c = ch[k];
         if (!c.active) continue;
-        if (!c.run) { aux[c.b].pad = c.st_seq; fse_publish(aux, c.b, FSE_PROGRESS_FINAL); continue; }
-        if (!c.bad) { fse_publish(aux, c.b, FSE_PROGRESS_FINAL); continue; }
+        if (!c.run) { aux[c.b].pad = c.st_seq; continue; }
+        if (!c.bad) continue;
         const uint16_t *TL = tabs + (FSE_CHAINS * lane + k) * FSE_TAB_U16;
         fse_exact_block(c.d, aux, c.b, input, seq_scratch, TL, TL + 512, TL + 1024, c.tl, c.to, c.tm, s_ll_base, s_ml_base, s_ll_bits, s_ml_bits, c.st_seq);
     }
@@ -912,8 +904,6 @@ __device__ uint32_t exec_batch_exact(ExecState &st, const LitSrc &lit, const Fra
     return 0;
 }
 
-// ---- hand-off from k_fse (see fse_publish).  Bounded polling: if the producer never shows up (it always does: k_fse is
-// launched first and fits on the device in one wave) the frame fails with an internal error instead of hanging the GPU.
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -930,22 +920,6 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) {
     asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// waits until at least `need` sequences of block b are published (or the block is final); returns the published count,
-// 0xFFFFFFFE on timeout.  Warp-uniform.
-__device__ __forceinline__ uint32_t exec_wait_progress(const BlockAux *aux, uint32_t b, uint32_t need, uint32_t lane) {
-    uint32_t v = 0;
-    if (lane == 0) {
-        uint32_t spins = 0;
-        for (;;) {
-            v = ld_acquire_u32(&aux[b].progress);
-            if (v >= need) break;
-            __nanosleep(128);
-            if (++spins > (1u << 22)) { v = 0xFFFFFFFEu; break; }
-        }
-    }
-    return __shfl_sync(0xffffffffu, v, 0);
-}
-
 #ifndef B200Z_EXEC_WARPS
 #define B200Z_EXEC_WARPS 4
 #endif
@@ -970,7 +944,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                                                         const FrameDesc *__restrict__ frames, FrameState *__restrict__ states,
                                                         const uint8_t *__restrict__ input, const uint8_t *__restrict__ lit_scratch,
                                                         const uint32_t *__restrict__ seq_scratch, uint8_t *__restrict__ output, uint64_t output_cap,
-                                                        uint32_t nframes) {
+                                                        uint32_t nframes, const uint32_t *__restrict__ resume) {
     __shared__ uint32_t s_mask[EXEC_WARPS][EXEC_MASK_WORDS];
     __shared__ __align__(16) uint2 s_recs[EXEC_WARPS][EXEC_BATCH];
     const uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -980,6 +954,9 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
     uint32_t a_recs = (uint32_t)__cvta_generic_to_shared(s_recs[threadIdx.x >> 5]);   // this warp's per-sequence records
     asm volatile("" : "+r"(a_mask), "+r"(a_recs));   // keep both addresses in registers (ptxas would recompute them from %tid per chunk)
     const FrameDesc &fd = frames[f];
+    // frames (or leading blocks of frames) that k_exec_cta already executed: resume[f] = first block left for this kernel
+    const uint32_t first_bi = resume ? resume[f] : 0u;
+    if (first_bi > fd.nblocks) return;   // k_exec_cta finished the frame, final state included
     FrameState fs = states[f];
     ExecState st;
     st.h0 = fs.hist[0]; st.h1 = fs.hist[1]; st.h2 = fs.hist[2];
@@ -989,7 +966,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
     uint8_t *out = output + fd.out_off;
     uint32_t status = fs.status, err_block = fs.error_block, blocks_done = fs.blocks_done;
 
-    for (uint32_t bi = 0; bi < fd.nblocks && !status; bi++) {
+    for (uint32_t bi = first_bi; bi < fd.nblocks && !status; bi++) {
         const uint32_t b = fd.first_block + bi;
         const BlockDesc &d = descs[b];
         // first error in the reference's order: header-level planner errors, literals, sequence header (planner),
@@ -1000,9 +977,9 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
         if (hs && hpos == 1) bs = hs;
         else if (aux[b].status) bs = aux[b].status;
         else if (hs) bs = hs;
-        // the sequence-stage status (aux.pad) is only known when k_fse has finished the block: checked after the
-        // sequences have been consumed; it takes precedence over an execution error, as in the reference where
-        // decode_sequences completes before execute_sequences starts (block_decoder.rs:176-183)
+        else if (d.btype == BT_COMPRESSED && d.nseq && aux[b].pad) bs = aux[b].pad;
+        // a block whose sequence stage failed executes nothing: in the reference decode_sequences completes before
+        // execute_sequences starts (block_decoder.rs:176-183)
         if (bs) { status = bs; err_block = d.block_in_frame; break; }
 
         if (d.btype == BT_RAW) {
@@ -1023,24 +1000,22 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
             uint32_t e = 0;
             // block-level descriptor fields used inside the batch loop are consumed here once: a first use inside the loop
             // would wait on a scoreboard shared with the record prefetch issued just before it (a full memory latency per batch)
-            uint32_t resolved_u = d.fse_resolves, nseq_u = d.nseq;
+            uint32_t resolved_u = (aux[b].flags & AUX_RAW_OFFSETS) ? 0u : 1u, nseq_u = d.nseq;
             const uint32_t *seqs = seq_scratch + d.seq_buf_off * 3;
             asm volatile("" : "+r"(resolved_u), "+r"(nseq_u), "+l"(seqs));
             const bool resolved = resolved_u != 0;
             __syncwarp();
-            // sequence records stream in from k_fse, which may still be decoding this block: `avail` = published count.
-            // A batch is EXEC_BATCH sequences, EXEC_PER_LANE consecutive ones per lane (contiguous 12-byte records); the next
-            // batch's records are requested into L2 one batch ahead.
+            // A batch is EXEC_BATCH sequences, EXEC_PER_LANE consecutive ones per lane (contiguous 12-byte records in prefix
+            // form {out_end, lit_end, of}: ll and ml are differences of neighbouring records); the next batch's records are
+            // requested into L2 one batch ahead.
             constexpr uint32_t K = EXEC_PER_LANE;
-            uint32_t avail = 0;
+            uint32_t carry_out = 0, carry_lit = 0;   // prefix sums at the end of the previous batch
+            const uint32_t bh0 = st.h0, bh1 = st.h1, bh2 = st.h2;   // history at the block's start: what the symbols refer to
             for (uint32_t base = 0; base < nseq_u && !e; base += EXEC_BATCH) {
                 const uint32_t nb = nseq_u - base < EXEC_BATCH ? nseq_u - base : EXEC_BATCH;
-                if (avail < base + nb) {
-                    avail = exec_wait_progress(aux, b, base + nb, lane);
-                    if (avail == 0xFFFFFFFEu) { e = B200Z_ERR_CUDA; break; }
-                }
-                uint32_t lls[K], mls[K], ofs[K];
+                uint32_t lls[K], mls[K], ofs[K], pe_out[K], pe_lit[K];
                 bool on[K];
+                const uint32_t old_out = carry_out, old_lit = carry_lit;
                 {
                     const uint32_t *sp = seqs + (uint64_t)(base + K * lane) * 3;
                     uint32_t raw[3 * K];
@@ -1054,32 +1029,38 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                             raw[3 * k] = have ? ld_cg_u32(sp + 3 * k) : 0u; raw[3 * k + 1] = have ? ld_cg_u32(sp + 3 * k + 1) : 0u; raw[3 * k + 2] = have ? ld_cg_u32(sp + 3 * k + 2) : 1u;
                         }
                     }
+                    // prefix form -> lengths: my first record's predecessor is the last record of the lane below (or the carry)
+                    uint32_t p_out = __shfl_up_sync(0xffffffffu, raw[3 * (K - 1)], 1), p_lit = __shfl_up_sync(0xffffffffu, raw[3 * (K - 1) + 1], 1);
+                    if (lane == 0) { p_out = carry_out; p_lit = carry_lit; }
 #pragma unroll
-                    for (uint32_t k = 0; k < K; k++) { on[k] = K * lane + k < nb; lls[k] = raw[3 * k]; mls[k] = raw[3 * k + 1]; ofs[k] = raw[3 * k + 2]; }
+                    for (uint32_t k = 0; k < K; k++) {
+                        on[k] = K * lane + k < nb;
+                        const uint32_t ll = raw[3 * k + 1] - p_lit, ml = raw[3 * k] - p_out - ll;
+                        lls[k] = on[k] ? ll : 0u; mls[k] = on[k] ? ml : 0u; ofs[k] = raw[3 * k + 2];
+                        p_out = raw[3 * k]; p_lit = raw[3 * k + 1];
+                        pe_out[k] = p_out; pe_lit[k] = p_lit;
+                    }
+                    {   // carry: the batch's last record
+                        const uint32_t lastl = (nb - 1) / K, lasts = (nb - 1) % K;
+                        uint32_t co = raw[0], cl = raw[1];
+#pragma unroll
+                        for (uint32_t k = 1; k < K; k++) { co = lasts == k ? raw[3 * k] : co; cl = lasts == k ? raw[3 * k + 1] : cl; }
+                        carry_out = __shfl_sync(0xffffffffu, co, lastl); carry_lit = __shfl_sync(0xffffffffu, cl, lastl);
+                    }
                     if (base + EXEC_BATCH < nseq_u && lane * 128u < (nseq_u - base - EXEC_BATCH) * 12u && lane * 128u < EXEC_BATCH * 12u)
                         prefetch_l2(reinterpret_cast<const uint8_t *>(seqs + (uint64_t)(base + EXEC_BATCH) * 3) + lane * 128u);
                 }
-                // inclusive scans of ll and ll + ml over the lanes' groups
-                uint32_t lit_end = 0, out_end = 0;
-#pragma unroll
-                for (uint32_t k = 0; k < K; k++) { lit_end += lls[k]; out_end += lls[k] + mls[k]; }
-#pragma unroll
-                for (int dd = 1; dd < 32; dd <<= 1) {
-                    uint32_t a = __shfl_up_sync(0xffffffffu, lit_end, dd), c = __shfl_up_sync(0xffffffffu, out_end, dd);
-                    if ((int)lane >= dd) { lit_end += a; out_end += c; }
-                }
-                const uint32_t T = __shfl_sync(0xffffffffu, out_end, 31), L = __shfl_sync(0xffffffffu, lit_end, 31);
+                // the records are prefix sums already (k_fse): batch totals and batch-relative positions are differences
+                const uint32_t T = carry_out - old_out, L = carry_lit - old_lit;
                 // per sequence: inclusive end of its bytes, start of its match, inclusive end of its literals (all batch-relative)
                 uint32_t oend[K], mstart[K], lend[K];
-                {
-                    uint32_t oe = out_end, le = lit_end;
 #pragma unroll
-                    for (int k = (int)K - 1; k >= 0; k--) { oend[k] = oe; lend[k] = le; mstart[k] = oe - mls[k]; oe -= lls[k] + mls[k]; le -= lls[k]; }
-                }
-                // offsets for the fast path must be resolved: blocks whose history is not a plan-time constant resolve here
+                for (uint32_t k = 0; k < K; k++) { oend[k] = on[k] ? pe_out[k] - old_out : T; lend[k] = on[k] ? pe_lit[k] - old_lit : L; mstart[k] = oend[k] - mls[k]; }
+                // actual offsets: symbols resolve against the history at the block's start; a block flagged AUX_RAW_OFFSETS
+                // (exact path of k_fse) runs do_offset_history here, sequence by sequence
                 uint32_t offs[K];
 #pragma unroll
-                for (uint32_t k = 0; k < K; k++) offs[k] = ofs[k];
+                for (uint32_t k = 0; k < K; k++) offs[k] = resolved ? seq_sym_resolve(ofs[k], bh0, bh1, bh2) : ofs[k];
                 uint32_t h0 = st.h0, h1 = st.h1, h2 = st.h2;
                 if (!resolved) {
                     // cheap scalar steps (sequence_execution.rs:59-118); committed only if the fast path is taken (the exact path
@@ -1103,7 +1084,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                 }
                 const bool fast = __all_sync(0xffffffffu, ok) && T <= EXEC_TMAX && (uint64_t)st.litpos + L <= lit.regen && st.produced + T <= st.cap && !lit.rle;
                 if (!fast) {
-                    e = exec_batch_exact(st, lit, fd, out, nb, lls, mls, ofs, resolved, lane);
+                    e = exec_batch_exact(st, lit, fd, out, nb, lls, mls, resolved ? offs : ofs, resolved, lane);
                     continue;
                 }
                 if (!resolved) { st.h0 = h0; st.h1 = h1; st.h2 = h2; }
@@ -1220,15 +1201,11 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                     st.produced += rest; st.counter += rest;
                 }
             }
-            if (d.nseq && !hs) {
-                // the block's sequence stage must be over before its verdict (and the history it resolved) can be read
-                uint32_t fin = exec_wait_progress(aux, b, FSE_PROGRESS_FINAL, lane);
-                uint32_t st_seq = ld_cg_u32(&aux[b].pad);
-                if (fin == 0xFFFFFFFEu) st_seq = mk_status(B200Z_ERR_CUDA, B200Z_STAGE_SEQUENCES);
-                if (st_seq) { status = st_seq; err_block = d.block_in_frame; break; }
-            }
             if (e) { status = mk_status(e, e == B200Z_ERR_TARGET_TOO_SMALL ? B200Z_STAGE_DRAIN : B200Z_STAGE_EXECUTE); err_block = d.block_in_frame; break; }
-            if (resolved && d.nseq) { st.h0 = ld_cg_u32(&aux[b].hist_after[0]); st.h1 = ld_cg_u32(&aux[b].hist_after[1]); st.h2 = ld_cg_u32(&aux[b].hist_after[2]); }
+            if (resolved && d.nseq) {   // the history after the block, in terms of the history at its start
+                const uint32_t a0 = aux[b].hist_after[0], a1 = aux[b].hist_after[1], a2 = aux[b].hist_after[2];
+                st.h0 = seq_sym_resolve(a0, bh0, bh1, bh2); st.h1 = seq_sym_resolve(a1, bh0, bh1, bh2); st.h2 = seq_sym_resolve(a2, bh0, bh1, bh2);
+            }
         }
         __syncwarp();
         blocks_done++;
@@ -1291,6 +1268,12 @@ __global__ void k_xxh64(const FrameDesc *__restrict__ frames, FrameState *__rest
     states[f].xxh64 = h;
 }
 
+}  // namespace b200z
+
+#include "exec_cta.cuh"
+
+namespace b200z {
+
 // ------------------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------------------
@@ -1304,19 +1287,34 @@ int launch_predefined(FseSlot *predef, cudaStream_t s) {
 constexpr uint32_t kHufSmem = HUF_BLOCKS_PER_CTA * HUF_SMEM_PER_BLOCK + 32 * RING_STRIDE;
 constexpr uint32_t kFseSmem = FSE_BLOCKS_PER_CTA * FSE_TAB_U16 * 2 + 1024 + FSE_BLOCKS_PER_CTA * RING_STRIDE;
 
+static int g_num_sms[64];   // per device ordinal, filled by init_kernels
+
 int init_kernels() {
     cudaError_t e = cudaFuncSetAttribute(k_fse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFseSmem);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_huf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHufSmem);
     if (e != cudaSuccess) return (int)e;
-    // k_fse and k_exec share SMs: ask for the largest shared-memory carve-out so that both fit
+    e = cudaFuncSetAttribute(k_exec_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XC_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    // k_fse and k_huf run side by side: ask for the largest shared-memory carve-out so that both fit
     e = cudaFuncSetAttribute(k_fse, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_exec, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-    return (int)e;
+    e = cudaFuncSetAttribute(k_huf, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < 64) g_num_sms[dev] = sms;
+    return 0;
 }
 
-const char *const kStageNames[kNumStages] = {"k_setup", "k_huf", "k_fse", "k_exec"};
+static uint32_t num_sms() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || g_num_sms[dev] <= 0) return 148;
+    return (uint32_t)g_num_sms[dev];
+}
+
+const char *const kStageNames[kNumStages] = {"k_setup", "k_huf", "k_fse", "k_exec_cta", "k_exec"};
 
 // one stage of the pipeline; a stage with nothing to do launches nothing and returns 0
 int launch_stage(const PipelineArgs &a, int stage, cudaStream_t s) {
@@ -1331,9 +1329,17 @@ int launch_stage(const PipelineArgs &a, int stage, cudaStream_t s) {
                 k_fse<<<cdiv(a.nblocks, FSE_BLOCKS_PER_CTA), 32, kFseSmem, s>>>(a.descs, a.aux, a.input, a.seq_scratch, a.nblocks);
             break;
         case 3:
+            // frames whose blocks are assembled in shared memory: persistent CTAs, one per SM, frames from a ticket counter
+            if (a.nframes && a.n_cta_frames)
+                k_exec_cta<<<a.n_cta_frames < num_sms() ? a.n_cta_frames : num_sms(), XC_THREADS, XC_SMEM_BYTES, s>>>(
+                    a.descs, a.aux, a.frames, a.states, a.input, a.lit_scratch, a.seq_scratch, a.output, a.output_cap, a.cta_frames, a.n_cta_frames, a.resume,
+                    a.ticket);
+            break;
+        case 4:
+            // every other frame, and whatever k_exec_cta left (resume[]): one warp per frame
             if (a.nframes)
                 k_exec<<<cdiv(a.nframes, EXEC_WARPS), EXEC_WARPS * 32, 0, s>>>(a.descs, a.aux, a.frames, a.states, a.input, a.lit_scratch, a.seq_scratch,
-                                                                a.output, a.output_cap, a.nframes);
+                                                                a.output, a.output_cap, a.nframes, a.resume);
             break;
         default: break;
     }
@@ -1345,40 +1351,40 @@ int launch_checksum(const PipelineArgs &a, cudaStream_t s) {
     return (int)cudaGetLastError();
 }
 
+// resume[] and the ticket counter start at zero for every pass
+static int reset_sched(const PipelineArgs &a, cudaStream_t s) {
+    if (!a.nframes || !a.ticket) return 0;
+    return (int)cudaMemsetAsync(a.ticket, 0, a.sched_bytes, s);
+}
+
 int launch_pipeline(const PipelineArgs &a, cudaStream_t s) {
+    if (int e = reset_sched(a, s)) return e;
     for (int st = 0; st < kNumStages; st++) { int e = launch_stage(a, st, s); if (e) return e; }
     return 0;
 }
 
-// k_exec runs beside k_fse and consumes its sequences through the per-block progress counters.  That is only safe if every
-// CTA of k_fse is resident before the first CTA of k_exec takes an SM: a k_exec CTA spins on blocks whose producer may not
-// have been placed yet, and an SM full of spinning consumers has no room for a producer (measured without the guarantee:
-// 4.4 -> 220 ms per pass when the hardware happened to place k_exec first).  Programmatic dependent launch gives exactly
-// that order: k_exec is launched in the same stream as a programmatic dependent of k_fse, whose CTAs all execute
-// griddepcontrol.launch_dependents as their first instruction; k_exec never calls griddepcontrol.wait -- the data hand-off is
-// the progress counters, and everything k_exec reads from k_setup / k_huf completed before k_fse started (stream order).
+// The two entropy stages are independent of each other (both only need k_setup's tables) and both are latency-bound chains
+// that leave most of the machine idle: k_huf runs on the side stream beside k_fse.  Execution follows when both are done.
 int launch_pipeline_overlapped(const PipelineArgs &a, const PipelineStreams &ps) {
     int e;
+    if ((e = reset_sched(a, ps.main))) return e;
     if ((e = launch_stage(a, 0, ps.main))) return e;
-    if ((e = launch_stage(a, 1, ps.main))) return e;
-    return launch_fse_exec(a, ps.main);
+    const bool fork = a.nblocks && ps.side && ps.fork && ps.join;
+    if (fork) {
+        if ((e = (int)cudaEventRecord(ps.fork, ps.main))) return e;
+        if ((e = (int)cudaStreamWaitEvent(ps.side, ps.fork, 0))) return e;
+        if ((e = launch_stage(a, 2, ps.main))) return e;   // k_fse first: every one of its CTAs must be resident (one wave)
+        if ((e = launch_stage(a, 1, ps.side))) return e;
+        if ((e = (int)cudaEventRecord(ps.join, ps.side))) return e;
+        if ((e = (int)cudaStreamWaitEvent(ps.main, ps.join, 0))) return e;
+    } else {
+        if ((e = launch_stage(a, 1, ps.main))) return e;
+        if ((e = launch_stage(a, 2, ps.main))) return e;
+    }
+    if ((e = launch_stage(a, 3, ps.main))) return e;
+    return launch_stage(a, 4, ps.main);
 }
 
-int launch_fse_exec(const PipelineArgs &a, cudaStream_t s) {
-    int e;
-    if ((e = launch_stage(a, 2, s))) return e;
-    if (!a.nframes) return 0;
-    if (!a.nblocks) return launch_stage(a, 3, s);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(cdiv(a.nframes, EXEC_WARPS)); cfg.blockDim = dim3(EXEC_WARPS * 32); cfg.dynamicSmemBytes = 0; cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return (int)cudaLaunchKernelEx(&cfg, k_exec, a.descs, (const BlockAux *)a.aux, a.frames, a.states, a.input, (const uint8_t *)a.lit_scratch,
-                                   (const uint32_t *)a.seq_scratch, a.output, a.output_cap, a.nframes);
-}
-
-uint32_t pipeline_launch_count(const PipelineArgs &a) { return (a.nblocks ? 3u : 0u) + (a.nframes ? 1u : 0u); }
+uint32_t pipeline_launch_count(const PipelineArgs &a) { return (a.nblocks ? 3u : 0u) + (a.nframes ? 1u : 0u) + (a.nframes && a.n_cta_frames ? 1u : 0u); }
 
 }  // namespace b200z

@@ -146,11 +146,6 @@ void plan_compressed_block(const uint8_t *c, uint32_t size, BlockDesc &d, BlockR
     cur.of = one_mode(mo, cur.of, r.build_fse);
     cur.ml = one_mode(mm, cur.ml, r.build_fse);
     r.ll = cur.ll; r.of = cur.of; r.ml = cur.ml;
-    if (cur.hist_known) {   // offset history at the start of this block is a plan-time constant (scratch.rs:44,53 / dictionary)
-        d.fse_resolves = 1;
-        d.init_hist[0] = cur.hist[0]; d.init_hist[1] = cur.hist[1]; d.init_hist[2] = cur.hist[2];
-        cur.hist_known = false;
-    }
     d.seq_buf_off = nseq_total;
     nseq_total += (nseq + 3) & ~3ull;   // keeps every block's sequence array 16-byte aligned (3 x u32 x 4)
 }

@@ -45,8 +45,6 @@ struct BlockRefs { TabRef huf, ll, of, ml; int32_t build_huf = -1, build_fse = -
 // "current tables" of a frame while planning (DecoderScratch.huf / .fse, scratch.rs:15-27)
 struct TableCursor {
     TabRef huf, ll, of, ml;
-    bool hist_known = false;   // the repeat-offset history is still the frame's initial one
-    uint32_t hist[3] = {1, 4, 8};
 };
 
 // Fills the section-level fields of `d` for a Compressed block whose content is content[0..size).
