@@ -8,7 +8,7 @@ import numpy as np
 XC_BATCH = 512
 XC_RING = 2048
 XC_WIN_MAX = 128 << 10
-XC_DATA_BYTES = 184 << 10
+XC_DATA_BYTES = 182 << 10
 SYM_SHIFT = 30
 
 
@@ -137,7 +137,7 @@ def exec_block(prefix_records, hist, literals, earlier, gaddr, loff=0):
         pend = np.zeros(128, dtype=bool)
         for j in range(128):
             s = int(src[j])
-            if mt[j] and s >= row_a:
+            if mt[j] and s >= max(row_a, woff):
                 pend[j] = True
             elif mt[j] and s < woff:
                 g = s - woff                       # relative to the block's first byte: negative

@@ -20,10 +20,13 @@
 // Output is then produced in ROWS of 128 bytes, one warp per row, FOUR bytes per lane: owner of the lane's first byte =
 // first64[chunk] + popc(mask bits below); a 4-byte word spans at most two sequences (match length >= 3), so two
 // records are fetched; each byte selects literal or match source and is read from shared memory; one aligned 32-bit
-// store per lane.  Rows whose sources lie in rows that are still in flight wait on a "rows done" bitmap (sources
-// always precede destinations, so the lowest unfinished row can always complete); sources inside the same row are
-// resolved inside the warp.  Overlapping matches use source = start + (k mod offset), the byte-order-preserving form
-// of repeat_in_chunks (decode_buffer.rs:113-141).
+// store per lane.  Match bytes whose source lies in rows that are being produced at the same time follow the TRUE byte
+// dependency, not the row order: every row publishes which of its bytes are still pending (four 32-bit planes per row,
+// plane k = ballot of "byte k of the lane's word is pending"); a byte is copied as soon as its source byte's bit is
+// clear.  Sources always precede destinations, so the lowest unfinished row can always complete; a row-to-row chain
+// (round 2's first version waited for whole rows: 400 k cycles per block) only forms where the data really chains.
+// Overlapping matches use source = start + (k mod offset), the byte-order-preserving form of repeat_in_chunks
+// (decode_buffer.rs:113-141).
 #pragma once
 
 namespace b200z {
@@ -33,18 +36,18 @@ constexpr uint32_t XC_BATCH = XC_THREADS;                  // sequences per batc
 constexpr uint32_t XC_RING = 2048;                         // record ring, 8-byte entries (4 batches)
 constexpr uint32_t XC_WIN_MAX = 128u << 10;                // largest block output handled here
 constexpr uint32_t XC_ROWS_MAX = XC_WIN_MAX / 128 + 1;     // + 1: the window starts at (global address & 15)
-constexpr uint32_t XC_DATA_BYTES = 184u << 10;             // window rows + staged literals
+constexpr uint32_t XC_DATA_BYTES = 182u << 10;             // window rows + staged literals
 constexpr uint32_t XC_MASK_BYTES = 16448;                  // >= XC_ROWS_MAX * 16, multiple of 64: one bit per window byte
 constexpr uint32_t XC_FIRST_BYTES = 8256;                  // >= XC_ROWS_MAX * 8: one u32 per 64 window bytes
-constexpr uint32_t XC_DONE_WORDS = 36;                     // >= XC_ROWS_MAX / 32 + 1 (+ slack for the frontier scan)
+constexpr uint32_t XC_PROWS = 256;                         // rows whose pending planes are live at once (a sub-phase)
 constexpr uint32_t XC_OFF_MASK = XC_DATA_BYTES;
 constexpr uint32_t XC_OFF_FIRST = XC_OFF_MASK + XC_MASK_BYTES;
 constexpr uint32_t XC_OFF_RING = XC_OFF_FIRST + XC_FIRST_BYTES;
-constexpr uint32_t XC_OFF_DONE = XC_OFF_RING + XC_RING * 8;
-constexpr uint32_t XC_OFF_MISC = XC_OFF_DONE + XC_DONE_WORDS * 4;
+constexpr uint32_t XC_OFF_PEND = XC_OFF_RING + XC_RING * 8;   // [XC_PROWS][4] u32
+constexpr uint32_t XC_OFF_MISC = XC_OFF_PEND + XC_PROWS * 16;
 constexpr uint32_t XC_SMEM_BYTES = XC_OFF_MISC + 128;
 static_assert(XC_SMEM_BYTES <= 232448, "k_exec_cta: more than 227 KiB of shared memory");
-static_assert(XC_MASK_BYTES >= XC_ROWS_MAX * 16 && XC_FIRST_BYTES >= XC_ROWS_MAX * 8 && XC_DONE_WORDS * 32 >= XC_ROWS_MAX + 64, "k_exec_cta tables");
+static_assert(XC_MASK_BYTES >= XC_ROWS_MAX * 16 && XC_FIRST_BYTES >= XC_ROWS_MAX * 8, "k_exec_cta tables");
 constexpr uint32_t XC_SPIN_LIMIT = 1u << 18;               // bounded waits: a stuck wait turns into a bail-out, never a hang
 
 struct XcMisc {               // at XC_OFF_MISC
@@ -73,6 +76,7 @@ __device__ __forceinline__ void xc_bulk_commit() { asm volatile("cp.async.bulk.c
 __device__ __forceinline__ void xc_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void xc_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void xc_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void xc_fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 __device__ __forceinline__ uint32_t xc_ld_acquire_shared(uint32_t a) { uint32_t v; asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ uint32_t xc_ldg_cg_u8(const uint8_t *p) { uint32_t v; asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
@@ -104,22 +108,11 @@ struct XcBlk {
     uint8_t *gout;       // global address of the block's first output byte
 };
 
-// number of leading finished rows (>= F: the cached value is a valid lower bound)
-__device__ __forceinline__ uint32_t xc_frontier(uint32_t S_done, uint32_t F, uint32_t lane) {
-    const uint32_t w0 = F >> 5;
-    const uint32_t idx = w0 + lane;
-    const uint32_t word = idx < XC_DONE_WORDS ? xc_ld_acquire_shared(S_done + (idx << 2)) : 0u;
-    const uint32_t nf = __ballot_sync(0xffffffffu, word != 0xFFFFFFFFu);
-    if (nf == 0) return (w0 + 32u) << 5;
-    const uint32_t first = (uint32_t)__ffs((int)nf) - 1u;
-    const uint32_t wv = __shfl_sync(0xffffffffu, word, first);
-    return ((w0 + first) << 5) + ((uint32_t)__ffs((int)~wv) - 1u);
-}
-
-// One row of 128 window bytes by one warp.  Returns false if a wait timed out.
+// One row of 128 window bytes by one warp.  `lo_a` = first window position of the current sub-phase: everything below
+// it is final.  Returns false if a wait timed out.
 template <bool FAR>
-__device__ __forceinline__ bool xc_row(const XcBlk &B, uint32_t r, uint32_t &F, bool has_ovl, uint32_t lane) {
-    const uint32_t S = B.S, S_mask = S + XC_OFF_MASK, S_first = S + XC_OFF_FIRST, S_ring = S + XC_OFF_RING, S_done = S + XC_OFF_DONE;
+__device__ __forceinline__ bool xc_row(const XcBlk &B, uint32_t r, uint32_t lo_a, bool has_ovl, uint32_t lane) {
+    const uint32_t S = B.S, S_mask = S + XC_OFF_MASK, S_first = S + XC_OFF_FIRST, S_ring = S + XC_OFF_RING, S_pend = S + XC_OFF_PEND;
     const uint32_t row_a = r << 7;
     const uint32_t a0 = row_a + (lane << 2);
     // ---- who owns my four bytes
@@ -132,68 +125,67 @@ __device__ __forceinline__ bool xc_row(const XcBlk &B, uint32_t r, uint32_t &F, 
     const uint32_t nib = (W >> sh) & 7u;   // sequence ends at my bytes 0..2: the following bytes belong to the next sequence
     const XcRec A = xc_unpack(lds64(S_ring + ((owner0 & (XC_RING - 1u)) << 3)));
     const XcRec Bn = xc_unpack(lds64(S_ring + (((owner0 + 1u) & (XC_RING - 1u)) << 3)));
+    // first position of the block in this sub-phase: sources below it are final (earlier sub-phases / phases), or -- below
+    // woff -- in earlier blocks of the frame (global memory)
+    const int32_t fin_a = (int32_t)max(lo_a, B.woff);
     int32_t src[4];
-    bool mt[4];
+    uint32_t word = 0, pend = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const bool useB = k > 0 && (nib & ((1u << k) - 1u)) != 0u;
         const uint32_t x = useB ? Bn.x : A.x, lz = useB ? Bn.lz : A.lz, noff = useB ? Bn.noff : A.noff;
         const uint32_t a = a0 + (uint32_t)k;
-        mt[k] = a >= x;
-        src[k] = (int32_t)(a + (mt[k] ? noff : lz));
+        const bool mt = a >= x;
+        src[k] = (int32_t)(a + (mt ? noff : lz));
         if (has_ovl) {   // overlapping match: byte kk comes from kk mod offset (warp-uniform branch, rare)
             const uint32_t kk = a - x, off = 0u - noff;
-            if (mt[k] && kk >= off) src[k] = (int32_t)(x - off + kk % off);
+            if (mt && kk >= off) src[k] = (int32_t)(x - off + kk % off);
         }
-    }
-    // ---- sources in rows that are still in flight: wait until the frontier has passed them
-    const int32_t row_s = (int32_t)row_a;
-    {
-        int32_t need = -1;   // highest source position outside this row
-#pragma unroll
-        for (int k = 0; k < 4; k++) if (mt[k] && src[k] < row_s) need = max(need, src[k]);
-        uint32_t spins = 0;
-        while (__any_sync(0xffffffffu, need >= (int32_t)(F << 7))) {
-            if (spins) __nanosleep(40);
-            F = xc_frontier(S_done, F, lane);
-            if (++spins > XC_SPIN_LIMIT) return false;
+        // source produced in this sub-phase: its row's pending plane says whether the byte is there yet (my own row's planes
+        // are still all-ones: in-row sources always go through the rounds below)
+        bool wait = mt && src[k] >= fin_a;
+        if (wait) {
+            const uint32_t sa = (uint32_t)src[k];
+            const uint32_t pm = xc_ld_acquire_shared(S_pend + (((sa >> 7) & (XC_PROWS - 1u)) << 4) + ((sa & 3u) << 2));
+            wait = ((pm >> ((sa >> 2) & 31u)) & 1u) != 0u;
         }
-    }
-    // ---- gather
-    uint32_t word = 0, pend = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const bool inrow = mt[k] && src[k] >= row_s;
         uint32_t v = 0;
         if (FAR) {
-            const bool far = mt[k] && src[k] < (int32_t)B.woff;
+            const bool far = mt && src[k] < (int32_t)B.woff;
             if (far) v = xc_ldg_cg_u8(B.gout + (src[k] - (int32_t)B.woff));
-            else if (!inrow) v = lds8(S + (uint32_t)src[k]);
-        } else if (!inrow) v = lds8(S + (uint32_t)src[k]);
+            else if (!wait) v = lds8(S + (uint32_t)src[k]);
+        } else if (!wait) v = lds8(S + (uint32_t)src[k]);
         word |= v << (8 * k);
-        pend |= inrow ? (1u << k) : 0u;
+        pend |= wait ? (1u << k) : 0u;
     }
-    if (!__any_sync(0xffffffffu, pend != 0u)) {
-        sts32(S + a0, word);
-    } else {
-        // bytes whose source lies in this very row: the lowest pending byte's source is never pending, so every round
-        // completes at least one byte; typical depth 1-2
-        sts32(S + a0, word);
+    const uint32_t P_row = S_pend + ((r & (XC_PROWS - 1u)) << 4);
+    if (__any_sync(0xffffffffu, pend != 0u)) {
+        // Bytes whose source is produced in this sub-phase.  Each round: a pending byte whose source byte is not pending (its
+        // row's plane bit is clear; inside this row: the ballot) is copied.  The lowest pending byte of the lowest unfinished
+        // row never depends on a pending byte, so the loops of all warps terminate.
         uint32_t spins = 0;
+        bool publish = true;
+        sts32(S + a0, word);
         for (;;) {
             __syncwarp();
             const uint32_t pm0 = __ballot_sync(0xffffffffu, pend & 1u), pm1 = __ballot_sync(0xffffffffu, pend & 2u),
                            pm2 = __ballot_sync(0xffffffffu, pend & 4u), pm3 = __ballot_sync(0xffffffffu, pend & 8u);
             if ((pm0 | pm1 | pm2 | pm3) == 0u) break;
+            if (publish) {
+                // the bytes that are there become visible to the rows that depend on them (data first, then the planes)
+                if (lane < 4) { xc_fence_cta(); sts32(P_row + (lane << 2), lane == 0 ? pm0 : (lane == 1 ? pm1 : (lane == 2 ? pm2 : pm3))); }
+            }
             bool changed = false;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 if (pend & (1u << k)) {
-                    const uint32_t rel = (uint32_t)(src[k] - row_s);
-                    const uint32_t sb = rel & 3u, sl = rel >> 2;
-                    const uint32_t pm = sb == 0 ? pm0 : (sb == 1 ? pm1 : (sb == 2 ? pm2 : pm3));
+                    const uint32_t sa = (uint32_t)src[k];
+                    const uint32_t sr = sa >> 7, sl = (sa >> 2) & 31u, sb = sa & 3u;
+                    uint32_t pm;
+                    if (sr == r) pm = sb == 0 ? pm0 : (sb == 1 ? pm1 : (sb == 2 ? pm2 : pm3));
+                    else pm = xc_ld_acquire_shared(S_pend + ((sr & (XC_PROWS - 1u)) << 4) + (sb << 2));
                     if (!((pm >> sl) & 1u)) {
-                        const uint32_t v = lds8(S + (uint32_t)src[k]);
+                        const uint32_t v = lds8(S + sa);
                         word = (word & ~(0xFFu << (8 * k))) | (v << (8 * k));
                         pend &= ~(1u << k);
                         changed = true;
@@ -201,20 +193,20 @@ __device__ __forceinline__ bool xc_row(const XcBlk &B, uint32_t r, uint32_t &F, 
                 }
             }
             if (changed) sts32(S + a0, word);
-            if (++spins > 4096u) return false;
+            publish = __any_sync(0xffffffffu, changed);
+            if (++spins > XC_SPIN_LIMIT) return false;
         }
+    } else {
+        sts32(S + a0, word);
+        __syncwarp();
     }
-    // ---- publish the row
-    __syncwarp();
-    if (lane == 0) {
-        __threadfence_block();
-        red_or_shared(S_done + ((r >> 5) << 2), 1u << (r & 31u));
-    }
+    // ---- publish: nothing of this row is pending any more
+    if (lane < 4) { xc_fence_cta(); sts32(P_row + (lane << 2), 0u); }
     return true;
 }
 
 // registers a thread carries from the record loads of a batch to its build step
-struct XcLoad { uint32_t cur_out, cur_lit, of, p_out, p_lit; };
+struct XcLoad { uint32_t cur_out, cur_lit, of, p_out, p_lit; };   // p_*: lane 0 only (the record before the warp's first)
 
 __device__ __forceinline__ XcLoad xc_load(const XcBlk &B, uint32_t k, uint32_t tid, uint32_t lane) {
     XcLoad L;
@@ -222,18 +214,20 @@ __device__ __forceinline__ XcLoad xc_load(const XcBlk &B, uint32_t k, uint32_t t
     L.cur_out = 0; L.cur_lit = 0; L.of = 0;
     if (i < B.nseq) { const uint32_t *p = B.seqs + (uint64_t)i * 3; L.cur_out = p[0]; L.cur_lit = p[1]; L.of = p[2]; }
     else if (i < B.ntot) { L.cur_out = B.out_size; L.cur_lit = B.regen; }   // trailing literals (sequence_execution.rs:40-44)
-    L.p_out = __shfl_up_sync(0xffffffffu, L.cur_out, 1); L.p_lit = __shfl_up_sync(0xffffffffu, L.cur_lit, 1);
-    if (lane == 0) {
-        if (i == 0 || i > B.nseq) { L.p_out = 0; L.p_lit = 0; }   // (i > nseq: the sentinel, which has no predecessor to look at)
-        else { const uint32_t *p = B.seqs + (uint64_t)(i - 1) * 3; L.p_out = p[0]; L.p_lit = p[1]; }
-    }
+    L.p_out = 0; L.p_lit = 0;
+    // (no shuffle here: the loads stay in flight while the rows of the previous batch are produced)
+    if (lane == 0 && i != 0 && i <= B.nseq) { const uint32_t *p = B.seqs + (uint64_t)(i - 1) * 3; L.p_out = p[0]; L.p_lit = p[1]; }
     return L;
 }
 
 // publishes sequence i = k * XC_BATCH + tid (record, end bit, chunk owners); validates what the rows rely on
-__device__ __forceinline__ void xc_build(const XcBlk &B, uint32_t k, uint32_t tid, const XcLoad &L, volatile XcMisc *misc) {
+__device__ __forceinline__ void xc_build(const XcBlk &B, uint32_t k, uint32_t tid, XcLoad L, volatile XcMisc *misc) {
     const uint32_t S = B.S, S_mask = S + XC_OFF_MASK, S_first = S + XC_OFF_FIRST, S_ring = S + XC_OFF_RING;
     const uint32_t i = k * XC_BATCH + tid;
+    {   // the record before mine: the lane below, or (lane 0) loaded by xc_load
+        const uint32_t po = __shfl_up_sync(0xffffffffu, L.cur_out, 1), pl = __shfl_up_sync(0xffffffffu, L.cur_lit, 1);
+        if ((tid & 31u) != 0) { L.p_out = po; L.p_lit = pl; }
+    }
     if (i > B.ntot) return;
     if (i == B.ntot) {
         // sentinel: bytes of the last row beyond the block copy themselves (never a match, literal delta 0)
@@ -355,7 +349,6 @@ __global__ void __launch_bounds__(XC_THREADS, 1) k_exec_cta(const BlockDesc *__r
             // that may read earlier output of its frame also needs those stores to be complete in global memory
             if (tid == 0) { if (has_far && !fresh) xc_bulk_wait0(); else xc_bulk_wait_read0(); }
             for (uint32_t j = tid; j < XC_MASK_BYTES / 16; j += XC_THREADS) sts128(S + XC_OFF_MASK + (j << 4), 0u, 0u, 0u, 0u);
-            if (tid < XC_DONE_WORDS) sts32(S + XC_OFF_DONE + (tid << 2), 0u);
             if (tid == 0) { misc->bail = 0; misc->ovl[0] = 0; misc->ovl[1] = 0; misc->ovl[2] = 0; misc->ovl[3] = 0; misc->end_a[0] = 0; misc->end_a[1] = 0; }
             __syncthreads();
             const bool tma_lit = lt != LT_RLE && regen != 0;
@@ -380,7 +373,7 @@ __global__ void __launch_bounds__(XC_THREADS, 1) k_exec_cta(const BlockDesc *__r
                 while (!xc_mbar_try_wait(S_mbar, lit_parity)) { if (++spins > XC_SPIN_LIMIT) { misc->bail = 2u; break; } }
                 lit_parity ^= 1u;
             }
-            uint32_t row_lo = 0, stored_a = (B.woff + 15u) & ~15u, F = 0;
+            uint32_t row_lo = 0, stored_a = (B.woff + 15u) & ~15u;
             for (uint32_t k = 0; k < nbatch && !blk_bail; k++) {
                 const bool last = k + 1 == nbatch;
                 XcLoad Ln;
@@ -388,10 +381,16 @@ __global__ void __launch_bounds__(XC_THREADS, 1) k_exec_cta(const BlockDesc *__r
                 const uint32_t row_hi = last ? B.nrows : (misc->end_a[k & 1u] >> 7);
                 const bool has_ovl = (misc->ovl[k & 3u] | misc->ovl[(k + 3u) & 3u]) != 0u;
                 if (tid == 0) misc->ovl[(k + 2u) & 3u] = 0u;
-                if (F < row_lo) F = row_lo;
                 bool ok = true;
-                for (uint32_t r = row_lo + warp; r < row_hi && ok; r += XC_WARPS)
-                    ok = has_far ? xc_row<true>(B, r, F, has_ovl, lane) : xc_row<false>(B, r, F, has_ovl, lane);
+                // sub-phases of at most XC_PROWS rows: their pending planes start all-ones, everything below is final
+                for (uint32_t lo = row_lo; lo < row_hi; lo += XC_PROWS) {
+                    const uint32_t hi = min(lo + XC_PROWS, row_hi);
+                    for (uint32_t j = tid; j < (hi - lo) * 4u; j += XC_THREADS) sts32(S + XC_OFF_PEND + ((((lo + (j >> 2)) & (XC_PROWS - 1u)) << 4) | ((j & 3u) << 2)), 0xFFFFFFFFu);
+                    __syncthreads();
+                    for (uint32_t r = lo + warp; r < hi && ok; r += XC_WARPS)
+                        ok = has_far ? xc_row<true>(B, r, lo << 7, has_ovl, lane) : xc_row<false>(B, r, lo << 7, has_ovl, lane);
+                    if (hi < row_hi) __syncthreads();   // the planes are re-used by the next sub-phase
+                }
                 if (!ok && lane == 0) misc->bail = 2u;
                 if (!last) xc_build(B, k + 1, tid, Ln, misc);
                 xc_fence_proxy_async();
