@@ -5,7 +5,7 @@ earlier blocks of the frame, in-row dependencies.  Rows are produced in order (t
 barriers -- is not modelled).  Test infrastructure only."""
 import numpy as np
 
-XC_BATCH = 512
+XC_BATCH = 1024
 XC_RING = 2048
 XC_WIN_MAX = 128 << 10
 XC_DATA_BYTES = 182 << 10

@@ -14,8 +14,8 @@
 //   * finished pieces leave as bulk stores shared -> global (cp.async.bulk, 16-byte aligned: the window is laid out
 //     at (global address & 15) so that shared and global alignment agree), overlapped with the rest of the block.
 // Work decomposition: sequences arrive in PREFIX form from k_fse ({out_end, lit_end, offset}), so any thread can place
-// any sequence without a scan.  A batch = 512 sequences, one per thread: the thread resolves its symbolic offset,
-// validates it, and publishes (a) an 8-byte record {match start, literal delta, offset} into a ring, (b) a bit at the
+// any sequence without a scan.  A batch = 1024 sequences, two per thread: the thread resolves the symbolic offsets,
+// validates them, and publishes per sequence (a) an 8-byte record {match start, literal delta, offset} into a ring, (b) a bit at the
 // sequence's last byte in a block-wide bitmask, (c) for every 64-byte chunk whose first byte it owns, its index.
 // Output is then produced in ROWS of 128 bytes, one warp per row, FOUR bytes per lane: owner of the lane's first byte =
 // first64[chunk] + popc(mask bits below); a 4-byte word spans at most two sequences (match length >= 3), so two
@@ -32,8 +32,9 @@
 namespace b200z {
 
 constexpr uint32_t XC_WARPS = 16, XC_THREADS = XC_WARPS * 32;
-constexpr uint32_t XC_BATCH = XC_THREADS;                  // sequences per batch, one per thread
-constexpr uint32_t XC_RING = 2048;                         // record ring, 8-byte entries (4 batches)
+constexpr uint32_t XC_PER_THREAD = 2;                      // consecutive sequences a thread publishes per batch
+constexpr uint32_t XC_BATCH = XC_THREADS * XC_PER_THREAD;  // sequences per batch
+constexpr uint32_t XC_RING = 2 * XC_BATCH;                 // record ring, 8-byte entries: the batch being produced + the next one
 constexpr uint32_t XC_WIN_MAX = 128u << 10;                // largest block output handled here
 constexpr uint32_t XC_ROWS_MAX = XC_WIN_MAX / 128 + 1;     // + 1: the window starts at (global address & 15)
 constexpr uint32_t XC_DATA_BYTES = 182u << 10;             // window rows + staged literals
@@ -108,126 +109,140 @@ struct XcBlk {
     uint8_t *gout;       // global address of the block's first output byte
 };
 
-// One row of 128 window bytes by one warp.  `lo_a` = first window position of the current sub-phase: everything below
-// it is final.  Returns false if a wait timed out.
-template <bool FAR>
-__device__ __forceinline__ bool xc_row(const XcBlk &B, uint32_t r, uint32_t lo_a, bool has_ovl, uint32_t lane) {
+__device__ __forceinline__ uint32_t xc_lds_volatile(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+
+// NR rows of 128 window bytes (rows r0, r0 + XC_WARPS, ...) by one warp, interleaved for instruction-level parallelism;
+// branch-free per byte.  `lo_a` = first window position of the current sub-phase: everything below it is final.
+// Returns false if a wait timed out.
+template <bool FAR, int NR>
+__device__ __forceinline__ bool xc_rows(const XcBlk &B, uint32_t r0, uint32_t lo_a, bool has_ovl, uint32_t lane) {
     const uint32_t S = B.S, S_mask = S + XC_OFF_MASK, S_first = S + XC_OFF_FIRST, S_ring = S + XC_OFF_RING, S_pend = S + XC_OFF_PEND;
-    const uint32_t row_a = r << 7;
-    const uint32_t a0 = row_a + (lane << 2);
-    // ---- who owns my four bytes
-    const uint32_t c = a0 >> 6;
-    const uint2 M = lds64(S_mask + (c << 3));
-    const bool hi_half = (a0 & 32u) != 0;
-    const uint32_t W = hi_half ? M.y : M.x;
-    const uint32_t sh = a0 & 31u;
-    const uint32_t owner0 = lds32(S_first + (c << 2)) + (uint32_t)__popc(W & ((1u << sh) - 1u)) + (hi_half ? (uint32_t)__popc(M.x) : 0u);
-    const uint32_t nib = (W >> sh) & 7u;   // sequence ends at my bytes 0..2: the following bytes belong to the next sequence
-    const XcRec A = xc_unpack(lds64(S_ring + ((owner0 & (XC_RING - 1u)) << 3)));
-    const XcRec Bn = xc_unpack(lds64(S_ring + (((owner0 + 1u) & (XC_RING - 1u)) << 3)));
     // first position of the block in this sub-phase: sources below it are final (earlier sub-phases / phases), or -- below
     // woff -- in earlier blocks of the frame (global memory)
     const int32_t fin_a = (int32_t)max(lo_a, B.woff);
-    int32_t src[4];
-    uint32_t word = 0, pend = 0;
+    uint32_t a0[NR], word[NR], pend[NR];
+    int32_t src[NR][4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const bool useB = k > 0 && (nib & ((1u << k) - 1u)) != 0u;
-        const uint32_t x = useB ? Bn.x : A.x, lz = useB ? Bn.lz : A.lz, noff = useB ? Bn.noff : A.noff;
-        const uint32_t a = a0 + (uint32_t)k;
-        const bool mt = a >= x;
-        src[k] = (int32_t)(a + (mt ? noff : lz));
-        if (has_ovl) {   // overlapping match: byte kk comes from kk mod offset (warp-uniform branch, rare)
-            const uint32_t kk = a - x, off = 0u - noff;
-            if (mt && kk >= off) src[k] = (int32_t)(x - off + kk % off);
+    for (int j = 0; j < NR; j++) {
+        const uint32_t r = r0 + (uint32_t)j * XC_WARPS;
+        a0[j] = (r << 7) + (lane << 2);
+        // ---- who owns my four bytes
+        const uint32_t c = a0[j] >> 6;
+        const uint2 M = lds64(S_mask + (c << 3));
+        const bool hi_half = (a0[j] & 32u) != 0;
+        const uint32_t W = hi_half ? M.y : M.x;
+        const uint32_t sh = a0[j] & 31u;
+        const uint32_t owner0 = lds32(S_first + (c << 2)) + (uint32_t)__popc(W & ((1u << sh) - 1u)) + (hi_half ? (uint32_t)__popc(M.x) : 0u);
+        const uint32_t nib = (W >> sh) & 7u;   // sequence ends at my bytes 0..2: the following bytes belong to the next sequence
+        const XcRec A = xc_unpack(lds64(S_ring + ((owner0 & (XC_RING - 1u)) << 3)));
+        const XcRec Bn = xc_unpack(lds64(S_ring + (((owner0 + 1u) & (XC_RING - 1u)) << 3)));
+        word[j] = 0; pend[j] = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const bool useB = k > 0 && (nib & ((1u << k) - 1u)) != 0u;
+            const uint32_t x = useB ? Bn.x : A.x, lz = useB ? Bn.lz : A.lz, noff = useB ? Bn.noff : A.noff;
+            const uint32_t a = a0[j] + (uint32_t)k;
+            const bool mt = a >= x;
+            src[j][k] = (int32_t)(a + (mt ? noff : lz));
+            if (has_ovl) {   // overlapping match: byte kk comes from kk mod offset (warp-uniform branch, rare)
+                const uint32_t kk = a - x, off = 0u - noff;
+                if (mt && kk >= off) src[j][k] = (int32_t)(x - off + kk % off);
+            }
+            // A source produced in this sub-phase: its row's pending plane says whether the byte is there yet (my own row's
+            // planes are still all-ones: in-row sources always go through the rounds below).  The plane word is read for every
+            // byte (any address inside the plane area is harmless) so that there is no branch.
+            const uint32_t sa = (uint32_t)src[j][k];
+            const uint32_t pm = xc_lds_volatile(S_pend + (((sa >> 7) & (XC_PROWS - 1u)) << 4) + ((sa & 3u) << 2));
+            const bool wait = mt && src[j][k] >= fin_a && ((pm >> ((sa >> 2) & 31u)) & 1u) != 0u;
+            const bool far = FAR && mt && src[j][k] < (int32_t)B.woff;
+            uint32_t v = lds8(S + ((wait || far) ? a : sa));   // (a byte that waits / comes from global memory reads itself: harmless)
+            if (FAR) { if (far) v = xc_ldg_cg_u8(B.gout + (src[j][k] - (int32_t)B.woff)); }
+            word[j] |= v << (8 * k);
+            pend[j] |= wait ? (1u << k) : 0u;
         }
-        // source produced in this sub-phase: its row's pending plane says whether the byte is there yet (my own row's planes
-        // are still all-ones: in-row sources always go through the rounds below)
-        bool wait = mt && src[k] >= fin_a;
-        if (wait) {
-            const uint32_t sa = (uint32_t)src[k];
-            const uint32_t pm = xc_ld_acquire_shared(S_pend + (((sa >> 7) & (XC_PROWS - 1u)) << 4) + ((sa & 3u) << 2));
-            wait = ((pm >> ((sa >> 2) & 31u)) & 1u) != 0u;
-        }
-        uint32_t v = 0;
-        if (FAR) {
-            const bool far = mt && src[k] < (int32_t)B.woff;
-            if (far) v = xc_ldg_cg_u8(B.gout + (src[k] - (int32_t)B.woff));
-            else if (!wait) v = lds8(S + (uint32_t)src[k]);
-        } else if (!wait) v = lds8(S + (uint32_t)src[k]);
-        word |= v << (8 * k);
-        pend |= wait ? (1u << k) : 0u;
     }
-    const uint32_t P_row = S_pend + ((r & (XC_PROWS - 1u)) << 4);
-    if (__any_sync(0xffffffffu, pend != 0u)) {
-        // Bytes whose source is produced in this sub-phase.  Each round: a pending byte whose source byte is not pending (its
-        // row's plane bit is clear; inside this row: the ballot) is copied.  The lowest pending byte of the lowest unfinished
-        // row never depends on a pending byte, so the loops of all warps terminate.
+    bool anyp = false;
+#pragma unroll
+    for (int j = 0; j < NR; j++) { sts32(S + a0[j], word[j]); anyp = anyp || pend[j] != 0u; }
+    if (__any_sync(0xffffffffu, anyp)) {
+        // Bytes whose source was not there yet.  Each round: publish which bytes are still pending (data first, then the
+        // planes), then copy every pending byte whose source byte is no longer pending.  The lowest pending byte of the lowest
+        // unfinished row never depends on a pending byte, so the loops of all warps terminate.
         uint32_t spins = 0;
         bool publish = true;
-        sts32(S + a0, word);
         for (;;) {
             __syncwarp();
-            const uint32_t pm0 = __ballot_sync(0xffffffffu, pend & 1u), pm1 = __ballot_sync(0xffffffffu, pend & 2u),
-                           pm2 = __ballot_sync(0xffffffffu, pend & 4u), pm3 = __ballot_sync(0xffffffffu, pend & 8u);
-            if ((pm0 | pm1 | pm2 | pm3) == 0u) break;
-            if (publish) {
-                // the bytes that are there become visible to the rows that depend on them (data first, then the planes)
-                if (lane < 4) { xc_fence_cta(); sts32(P_row + (lane << 2), lane == 0 ? pm0 : (lane == 1 ? pm1 : (lane == 2 ? pm2 : pm3))); }
-            }
-            bool changed = false;
+            uint32_t pm[NR][4], left = 0;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (pend & (1u << k)) {
-                    const uint32_t sa = (uint32_t)src[k];
-                    const uint32_t sr = sa >> 7, sl = (sa >> 2) & 31u, sb = sa & 3u;
-                    uint32_t pm;
-                    if (sr == r) pm = sb == 0 ? pm0 : (sb == 1 ? pm1 : (sb == 2 ? pm2 : pm3));
-                    else pm = xc_ld_acquire_shared(S_pend + ((sr & (XC_PROWS - 1u)) << 4) + (sb << 2));
-                    if (!((pm >> sl) & 1u)) {
-                        const uint32_t v = lds8(S + sa);
-                        word = (word & ~(0xFFu << (8 * k))) | (v << (8 * k));
-                        pend &= ~(1u << k);
-                        changed = true;
+            for (int j = 0; j < NR; j++) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) { pm[j][k] = __ballot_sync(0xffffffffu, (pend[j] >> k) & 1u); left |= pm[j][k]; }
+            }
+            if (left == 0u) break;
+            if (publish) {
+                if (lane < 4) {
+                    xc_fence_cta();
+#pragma unroll
+                    for (int j = 0; j < NR; j++) {
+                        const uint32_t r = r0 + (uint32_t)j * XC_WARPS;
+                        sts32(S_pend + ((r & (XC_PROWS - 1u)) << 4) + (lane << 2), lane == 0 ? pm[j][0] : (lane == 1 ? pm[j][1] : (lane == 2 ? pm[j][2] : pm[j][3])));
                     }
                 }
+                __syncwarp();
+            } else __nanosleep(20);
+            bool changed = false;
+#pragma unroll
+            for (int j = 0; j < NR; j++) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t sa = (uint32_t)src[j][k];
+                    const uint32_t pw = xc_lds_volatile(S_pend + (((sa >> 7) & (XC_PROWS - 1u)) << 4) + ((sa & 3u) << 2));
+                    const bool ready = ((pend[j] >> k) & 1u) != 0u && ((pw >> ((sa >> 2) & 31u)) & 1u) == 0u;
+                    const uint32_t v = lds8(S + (ready ? sa : a0[j] + (uint32_t)k));
+                    const uint32_t m = 0xFFu << (8 * k);
+                    word[j] = ready ? ((word[j] & ~m) | (v << (8 * k))) : word[j];
+                    pend[j] &= ready ? ~(1u << k) : 0xFFFFFFFFu;
+                    changed = changed || ready;
+                }
+                sts32(S + a0[j], word[j]);
             }
-            if (changed) sts32(S + a0, word);
             publish = __any_sync(0xffffffffu, changed);
             if (++spins > XC_SPIN_LIMIT) return false;
         }
-    } else {
-        sts32(S + a0, word);
-        __syncwarp();
+    } else __syncwarp();
+    // ---- publish: nothing of these rows is pending any more
+    if (lane < 4) {
+        xc_fence_cta();
+#pragma unroll
+        for (int j = 0; j < NR; j++) sts32(S_pend + (((r0 + (uint32_t)j * XC_WARPS) & (XC_PROWS - 1u)) << 4) + (lane << 2), 0u);
     }
-    // ---- publish: nothing of this row is pending any more
-    if (lane < 4) { xc_fence_cta(); sts32(P_row + (lane << 2), 0u); }
     return true;
 }
 
-// registers a thread carries from the record loads of a batch to its build step
-struct XcLoad { uint32_t cur_out, cur_lit, of, p_out, p_lit; };   // p_*: lane 0 only (the record before the warp's first)
+// registers a thread carries from the record loads of a batch to its build step: XC_PER_THREAD consecutive records,
+// and (lane 0 only) the record before the warp's first
+struct XcLoad { uint32_t out[XC_PER_THREAD], lit[XC_PER_THREAD], of[XC_PER_THREAD], p_out, p_lit; };
 
 __device__ __forceinline__ XcLoad xc_load(const XcBlk &B, uint32_t k, uint32_t tid, uint32_t lane) {
     XcLoad L;
-    const uint32_t i = k * XC_BATCH + tid;
-    L.cur_out = 0; L.cur_lit = 0; L.of = 0;
-    if (i < B.nseq) { const uint32_t *p = B.seqs + (uint64_t)i * 3; L.cur_out = p[0]; L.cur_lit = p[1]; L.of = p[2]; }
-    else if (i < B.ntot) { L.cur_out = B.out_size; L.cur_lit = B.regen; }   // trailing literals (sequence_execution.rs:40-44)
+    const uint32_t i0 = k * XC_BATCH + tid * XC_PER_THREAD;
+#pragma unroll
+    for (uint32_t q = 0; q < XC_PER_THREAD; q++) {
+        const uint32_t i = i0 + q;
+        L.out[q] = 0; L.lit[q] = 0; L.of[q] = 0;
+        if (i < B.nseq) { const uint32_t *p = B.seqs + (uint64_t)i * 3; L.out[q] = p[0]; L.lit[q] = p[1]; L.of[q] = p[2]; }
+        else if (i < B.ntot) { L.out[q] = B.out_size; L.lit[q] = B.regen; }   // trailing literals (sequence_execution.rs:40-44)
+    }
     L.p_out = 0; L.p_lit = 0;
     // (no shuffle here: the loads stay in flight while the rows of the previous batch are produced)
-    if (lane == 0 && i != 0 && i <= B.nseq) { const uint32_t *p = B.seqs + (uint64_t)(i - 1) * 3; L.p_out = p[0]; L.p_lit = p[1]; }
+    if (lane == 0 && i0 != 0 && i0 <= B.nseq) { const uint32_t *p = B.seqs + (uint64_t)(i0 - 1) * 3; L.p_out = p[0]; L.p_lit = p[1]; }
     return L;
 }
 
-// publishes sequence i = k * XC_BATCH + tid (record, end bit, chunk owners); validates what the rows rely on
-__device__ __forceinline__ void xc_build(const XcBlk &B, uint32_t k, uint32_t tid, XcLoad L, volatile XcMisc *misc) {
+// publishes one sequence (record, end bit, chunk owners); validates what the rows rely on
+__device__ __forceinline__ void xc_build_one(const XcBlk &B, uint32_t k, uint32_t i, uint32_t cur_out, uint32_t cur_lit, uint32_t of, uint32_t p_out, uint32_t p_lit,
+                                             volatile XcMisc *misc) {
     const uint32_t S = B.S, S_mask = S + XC_OFF_MASK, S_first = S + XC_OFF_FIRST, S_ring = S + XC_OFF_RING;
-    const uint32_t i = k * XC_BATCH + tid;
-    {   // the record before mine: the lane below, or (lane 0) loaded by xc_load
-        const uint32_t po = __shfl_up_sync(0xffffffffu, L.cur_out, 1), pl = __shfl_up_sync(0xffffffffu, L.cur_lit, 1);
-        if ((tid & 31u) != 0) { L.p_out = po; L.p_lit = pl; }
-    }
     if (i > B.ntot) return;
     if (i == B.ntot) {
         // sentinel: bytes of the last row beyond the block copy themselves (never a match, literal delta 0)
@@ -238,27 +253,44 @@ __device__ __forceinline__ void xc_build(const XcBlk &B, uint32_t k, uint32_t ti
         return;
     }
     const bool real = i < B.nseq;
-    const uint32_t ll = L.cur_lit - L.p_lit, start = L.p_out, end = L.cur_out;
+    const uint32_t ll = cur_lit - p_lit, start = p_out, end = cur_out;
     const uint32_t mstart = start + ll;
     const uint32_t ml = end - mstart;
-    const uint32_t off = real ? seq_sym_resolve(L.of, B.h0, B.h1, B.h2) : 1u;
+    const uint32_t off = real ? seq_sym_resolve(of, B.h0, B.h1, B.h2) : 1u;
     // everything the rows rely on: positions inside the block, literals inside the literal buffer, offsets inside the
     // frame's earlier output.  (Zero offsets, dictionary reach, offsets beyond the buffer: the warp kernel reports
     // ExecuteSequencesError / DecodeBufferError exactly as the reference does.)
-    bool bad = end > B.out_size || end <= start || mstart > end || L.cur_lit > B.regen || L.cur_lit < L.p_lit;
+    bool bad = end > B.out_size || end <= start || mstart > end || cur_lit > B.regen || cur_lit < p_lit;
     if (real) bad = bad || off == 0u || off >= (1u << 28) || (uint64_t)off > B.reach + mstart || ml < 3u;
     if (bad) { misc->bail = 1u; return; }
     if (off < ml) misc->ovl[k & 3u] = 1u;
     const uint32_t start_a = B.woff + start, end_a = B.woff + end;
     // literal j of the block sits at shared offset lit_s + j; literal byte at window position a is literal number
     // (a - woff) - (match bytes before this sequence) = a - woff - (mstart - cur_lit)
-    const uint32_t lz = B.lit_s + L.cur_lit - B.woff - mstart;
+    const uint32_t lz = B.lit_s + cur_lit - B.woff - mstart;
     const uint2 rec = xc_pack(B.woff + mstart, lz, off);
     sts64(S_ring + ((i & (XC_RING - 1u)) << 3), rec.x, rec.y);
     red_or_shared(S_mask + (((end_a - 1u) >> 5) << 2), 1u << ((end_a - 1u) & 31u));
     const uint32_t c_lo = i == 0 ? 0u : (start_a + 63u) >> 6, c_hi = (end_a - 1u) >> 6;
     for (uint32_t c = c_lo; c <= c_hi; c++) sts32(S_first + (c << 2), i);
     if (i + 1 == (k + 1) * XC_BATCH) misc->end_a[k & 1u] = end_a;   // the batch's last sequence (a later batch exists: the sentinel)
+}
+
+__device__ __forceinline__ void xc_build(const XcBlk &B, uint32_t k, uint32_t tid, const XcLoad &L, volatile XcMisc *misc) {
+    const uint32_t i0 = k * XC_BATCH + tid * XC_PER_THREAD;
+    // the record before my first: the last record of the lane below, or (lane 0) loaded by xc_load
+    uint32_t p_out = __shfl_up_sync(0xffffffffu, L.out[XC_PER_THREAD - 1], 1), p_lit = __shfl_up_sync(0xffffffffu, L.lit[XC_PER_THREAD - 1], 1);
+    if ((tid & 31u) == 0) { p_out = L.p_out; p_lit = L.p_lit; }
+#pragma unroll
+    for (uint32_t q = 0; q < XC_PER_THREAD; q++) {
+        xc_build_one(B, k, i0 + q, L.out[q], L.lit[q], L.of[q], p_out, p_lit, misc);
+        p_out = L.out[q]; p_lit = L.lit[q];
+    }
+}
+
+// all pending planes = "pending": done between phases (everything below the next phase's first row is final and is never looked up)
+__device__ __forceinline__ void xc_planes_reset(uint32_t S, uint32_t tid) {
+    for (uint32_t j = tid; j < XC_PROWS * 4u / 2u; j += XC_THREADS) sts64(S + XC_OFF_PEND + (j << 3), 0xFFFFFFFFu, 0xFFFFFFFFu);
 }
 
 __global__ void __launch_bounds__(XC_THREADS, 1) k_exec_cta(const BlockDesc *__restrict__ descs, const BlockAux *__restrict__ aux,
@@ -365,6 +397,7 @@ __global__ void __launch_bounds__(XC_THREADS, 1) k_exec_cta(const BlockDesc *__r
             {
                 const XcLoad L0 = xc_load(B, 0, tid, lane);
                 xc_build(B, 0, tid, L0, misc);
+                xc_planes_reset(S, tid);
             }
             __syncthreads();
             bool blk_bail = misc->bail != 0;
@@ -382,30 +415,34 @@ __global__ void __launch_bounds__(XC_THREADS, 1) k_exec_cta(const BlockDesc *__r
                 const bool has_ovl = (misc->ovl[k & 3u] | misc->ovl[(k + 3u) & 3u]) != 0u;
                 if (tid == 0) misc->ovl[(k + 2u) & 3u] = 0u;
                 bool ok = true;
-                // sub-phases of at most XC_PROWS rows: their pending planes start all-ones, everything below is final
+                // sub-phases of at most XC_PROWS rows (their pending planes are all-ones when they start, everything below is final)
                 for (uint32_t lo = row_lo; lo < row_hi; lo += XC_PROWS) {
                     const uint32_t hi = min(lo + XC_PROWS, row_hi);
-                    for (uint32_t j = tid; j < (hi - lo) * 4u; j += XC_THREADS) sts32(S + XC_OFF_PEND + ((((lo + (j >> 2)) & (XC_PROWS - 1u)) << 4) | ((j & 3u) << 2)), 0xFFFFFFFFu);
-                    __syncthreads();
-                    for (uint32_t r = lo + warp; r < hi && ok; r += XC_WARPS)
-                        ok = has_far ? xc_row<true>(B, r, lo << 7, has_ovl, lane) : xc_row<false>(B, r, lo << 7, has_ovl, lane);
-                    if (hi < row_hi) __syncthreads();   // the planes are re-used by the next sub-phase
+                    if (lo != row_lo) { __syncthreads(); xc_planes_reset(S, tid); __syncthreads(); }
+                    uint32_t r = lo + warp;
+                    for (; r + XC_WARPS < hi && ok; r += 2 * XC_WARPS)
+                        ok = has_far ? xc_rows<true, 2>(B, r, lo << 7, has_ovl, lane) : xc_rows<false, 2>(B, r, lo << 7, has_ovl, lane);
+                    if (r < hi && ok) ok = has_far ? xc_rows<true, 1>(B, r, lo << 7, has_ovl, lane) : xc_rows<false, 1>(B, r, lo << 7, has_ovl, lane);
                 }
                 if (!ok && lane == 0) misc->bail = 2u;
-                if (!last) xc_build(B, k + 1, tid, Ln, misc);
                 xc_fence_proxy_async();
-                __syncthreads();
-                blk_bail = misc->bail != 0;
+                __syncthreads();   // the rows of this batch are final; nobody reads the previous batch's records any more
                 row_lo = row_hi;
                 // ---- rows below row_hi are final: send the aligned part to global memory while the next batch runs
                 uint32_t hi_a = min(row_hi << 7, B.a_end) & ~15u;
-                if (!blk_bail && hi_a > stored_a) {
+                if (misc->bail == 0 && hi_a > stored_a) {
                     if (tid == 0) {
                         for (uint32_t o = stored_a; o < hi_a; o += 32768u) xc_bulk_s2g(B.gout + (o - B.woff), S + o, min(32768u, hi_a - o));
                         xc_bulk_commit();
                     }
                     stored_a = hi_a;
                 }
+                if (!last) {
+                    xc_planes_reset(S, tid);
+                    xc_build(B, k + 1, tid, Ln, misc);
+                    __syncthreads();
+                }
+                blk_bail = misc->bail != 0;
             }
             if (blk_bail) { bailed = true; break; }
             // ---- head / tail bytes around the 16-byte aligned part
