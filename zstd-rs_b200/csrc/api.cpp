@@ -267,8 +267,10 @@ struct Submission {
         if ((e = d_fse.ensure((size_t)n_fse * sizeof(FseSlot)))) return e;
         if ((e = d_lit.ensure(lit_bytes + 64))) return e;
         if ((e = d_seq.ensure((nseq + 4) * 12))) return e;
-        // which execution kernel takes a frame: k_exec_cta assembles blocks in shared memory with a whole CTA -- right for
-        // anything but tiny frames; frames with a dictionary stay with the warp kernel (dictionary reach is its exact path).
+        // which execution kernel takes a frame.  A frame's blocks are a serial chain (window + offset history): k_exec_cta puts a
+        // whole CTA on the chain (block assembled in shared memory), k_exec one warp.  Many independent single-block frames are
+        // faster with one warp each (no cross-warp dependencies, all frames in flight); a multi-block frame is ~15x faster with the
+        // CTA.  Frames with a dictionary stay with the warp kernel (dictionary reach is its exact path).
         // B200Z_EXEC_MODE = warp | cta | auto (default) overrides for tests and measurements.
         cta_frames.clear();
         {
@@ -279,7 +281,7 @@ struct Submission {
                 if (fd.dict || fd.nblocks == 0) continue;
                 uint64_t src = 0;
                 for (uint32_t k = 0; k < fd.nblocks; k++) src += descs[fd.first_block + k].src_size;
-                if (force_cta || src >= 2048) cta_frames.push_back((uint32_t)f);
+                if (force_cta || (fd.nblocks >= 2 && src >= 4096)) cta_frames.push_back((uint32_t)f);
             }
         }
         if ((e = d_sched.ensure(16 + 4 * (frames.size() + cta_frames.size()) + 16))) return e;
