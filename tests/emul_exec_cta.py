@@ -10,6 +10,7 @@ XC_RING = 2048
 XC_WIN_MAX = 128 << 10
 XC_DATA_BYTES = 182 << 10
 SYM_SHIFT = 30
+XC_LITG_BIAS = (1 << 17) + 64
 
 
 def sym_resolve(v, h):
@@ -56,12 +57,12 @@ def exec_block(prefix_records, hist, literals, earlier, gaddr, loff=0):
     nrows = wbytes >> 7
     ntot = nseq + (1 if regen > sum_ll else 0)
     lit_bytes = (loff + regen + 15) & ~15
-    if wbytes + lit_bytes > XC_DATA_BYTES:
-        raise Bail("literals do not fit")
+    litg = wbytes + lit_bytes > XC_DATA_BYTES      # literals read from "global memory" (the bytes object) byte by byte
     lit_s = wbytes + loff
     reach = len(earlier)
     data = bytearray(XC_DATA_BYTES)
-    data[lit_s:lit_s + regen] = literals
+    if not litg:
+        data[lit_s:lit_s + regen] = literals
     mask = np.zeros(nrows * 128 + 64, dtype=np.uint8)      # one entry per window byte (the kernel packs them 32 per word)
     first = np.full(nrows * 2, 0xDEADBEEF, dtype=np.int64)
     ring = [(0x12345678, 0x9ABCDEF0)] * XC_RING            # stale garbage
@@ -100,7 +101,7 @@ def exec_block(prefix_records, hist, literals, earlier, gaddr, loff=0):
             if off < ml:
                 ovl[k & 3] = 1
             start_a, end_a = woff + start, woff + end
-            lz = lit_s + cur_lit - woff - mstart
+            lz = (XC_LITG_BIAS if litg else lit_s) + cur_lit - woff - mstart
             assert 0 <= lz < (1 << 18)
             ring[i & (XC_RING - 1)] = pack(woff + mstart, lz, off)
             mask[end_a - 1] = 1
@@ -143,6 +144,8 @@ def exec_block(prefix_records, hist, literals, earlier, gaddr, loff=0):
                 g = s - woff                       # relative to the block's first byte: negative
                 assert -g <= reach, "far source beyond the reachable output"
                 vals[j] = earlier[len(earlier) + g]
+            elif litg and not mt[j]:
+                vals[j] = literals[min((s - XC_LITG_BIAS) & 0xFFFFFFFF, regen - 1)]
             else:
                 assert 0 <= s < XC_DATA_BYTES
                 vals[j] = data[s]

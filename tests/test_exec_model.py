@@ -60,7 +60,9 @@ def test_model_on_synthetic(oracle):
     text = b" ".join(words[int(i)] for i in rng.integers(0, 300, 9000))[:48000]
     runs = b"".join(bytes([int(rng.integers(0, 256))]) * int(rng.integers(1, 700)) for _ in range(60)) + b"abcabcabc" * 500 + b"xy" * 3000
     chained = (text * 4)[:150000]   # > 128 KiB: two chained blocks, matches reach into the first block
-    for plain, mb in ((text, None), (runs, None), (chained, None)):
+    # a block that is nearly all literals (low-entropy bytes without matches): the literals do not fit beside the window
+    lowent = bytes(rng.choice(np.arange(40, 56, dtype=np.uint8), 126000, p=np.arange(1, 17) / 136.0)) + text[:4000]
+    for plain, mb in ((text, None), (runs, None), (chained, None), (lowent, None)):
         frame = G.compress(np.frombuffer(plain, dtype=np.uint8), level=3)
         nb, ns = _run_frame(oracle, frame, mb)
         assert nb >= 1

@@ -107,14 +107,16 @@ struct XcBlk {
     uint64_t reach;      // bytes of earlier output of the frame a match may reach back into (produced - drained)
     const uint32_t *seqs;
     uint8_t *gout;       // global address of the block's first output byte
+    const uint8_t *lit_gp;  // literals too large to stage beside the window: global address of literal 0 (else null)
 };
+constexpr uint32_t XC_LITG_BIAS = (1u << 17) + 64u;   // keeps the literal delta of the global-literals mode non-negative (18 bits)
 
 __device__ __forceinline__ uint32_t xc_lds_volatile(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 
 // NR rows of 128 window bytes (rows r0, r0 + XC_WARPS, ...) by one warp, interleaved for instruction-level parallelism;
 // branch-free per byte.  `lo_a` = first window position of the current sub-phase: everything below it is final.
 // Returns false if a wait timed out.
-template <bool FAR, int NR>
+template <bool FAR, bool LITG, int NR>
 __device__ __forceinline__ bool xc_rows(const XcBlk &B, uint32_t r0, uint32_t lo_a, bool has_ovl, uint32_t lane) {
     const uint32_t S = B.S, S_mask = S + XC_OFF_MASK, S_first = S + XC_OFF_FIRST, S_ring = S + XC_OFF_RING, S_pend = S + XC_OFF_PEND;
     // first position of the block in this sub-phase: sources below it are final (earlier sub-phases / phases), or -- below
@@ -155,8 +157,10 @@ __device__ __forceinline__ bool xc_rows(const XcBlk &B, uint32_t r0, uint32_t lo
             const uint32_t pm = xc_lds_volatile(S_pend + (((sa >> 7) & (XC_PROWS - 1u)) << 4) + ((sa & 3u) << 2));
             const bool wait = mt && src[j][k] >= fin_a && ((pm >> ((sa >> 2) & 31u)) & 1u) != 0u;
             const bool far = FAR && mt && src[j][k] < (int32_t)B.woff;
-            uint32_t v = lds8(S + ((wait || far) ? a : sa));   // (a byte that waits / comes from global memory reads itself: harmless)
+            const bool litg = LITG && !mt;   // literals read from global memory: src = literal index + XC_LITG_BIAS
+            uint32_t v = lds8(S + ((wait || far || litg) ? a : sa));   // (a byte that waits / comes from global memory reads itself: harmless)
             if (FAR) { if (far) v = xc_ldg_cg_u8(B.gout + (src[j][k] - (int32_t)B.woff)); }
+            if (LITG) { if (litg) v = __ldg(B.lit_gp + min(sa - XC_LITG_BIAS, B.regen - 1u)); }   // (clamp: bytes outside the block in the first / last row)
             word[j] |= v << (8 * k);
             pend[j] |= wait ? (1u << k) : 0u;
         }
@@ -267,7 +271,7 @@ __device__ __forceinline__ void xc_build_one(const XcBlk &B, uint32_t k, uint32_
     const uint32_t start_a = B.woff + start, end_a = B.woff + end;
     // literal j of the block sits at shared offset lit_s + j; literal byte at window position a is literal number
     // (a - woff) - (match bytes before this sequence) = a - woff - (mstart - cur_lit)
-    const uint32_t lz = B.lit_s + cur_lit - B.woff - mstart;
+    const uint32_t lz = (B.lit_gp ? XC_LITG_BIAS : B.lit_s) + cur_lit - B.woff - mstart;
     const uint2 rec = xc_pack(B.woff + mstart, lz, off);
     sts64(S_ring + ((i & (XC_RING - 1u)) << 3), rec.x, rec.y);
     red_or_shared(S_mask + (((end_a - 1u) >> 5) << 2), 1u << ((end_a - 1u) & 31u));
@@ -374,7 +378,10 @@ __global__ void __launch_bounds__(XC_THREADS, 1) k_exec_cta(const BlockDesc *__r
             if (lt == LT_RAW) { const uint8_t *p = input + d.src_off + d.lit_off; loff = (uint32_t)((uintptr_t)p & 15u); lit_g = p - loff; }
             else if (lt != LT_RLE) lit_g = lit_scratch + d.lit_buf_off;
             const uint32_t lit_bytes = (loff + regen + 15u) & ~15u;
-            if (wbytes + lit_bytes > XC_DATA_BYTES) { bailed = true; break; }
+            // literals that do not fit beside the window are read from global memory byte by byte (a block that is nearly all literals)
+            const bool litg = wbytes + lit_bytes > XC_DATA_BYTES;
+            if (litg && lt == LT_RLE) { bailed = true; break; }
+            B.lit_gp = litg ? lit_g + loff : nullptr;
             B.lit_s = wbytes + loff;
             const bool has_far = B.reach != 0;
             // ---- the window and the literal area are free once the previous block's bulk stores have read them; a block
@@ -383,7 +390,7 @@ __global__ void __launch_bounds__(XC_THREADS, 1) k_exec_cta(const BlockDesc *__r
             for (uint32_t j = tid; j < XC_MASK_BYTES / 16; j += XC_THREADS) sts128(S + XC_OFF_MASK + (j << 4), 0u, 0u, 0u, 0u);
             if (tid == 0) { misc->bail = 0; misc->ovl[0] = 0; misc->ovl[1] = 0; misc->ovl[2] = 0; misc->ovl[3] = 0; misc->end_a[0] = 0; misc->end_a[1] = 0; }
             __syncthreads();
-            const bool tma_lit = lt != LT_RLE && regen != 0;
+            const bool tma_lit = lt != LT_RLE && regen != 0 && !litg;
             if (tma_lit) {
                 if (tid == 0) {
                     xc_mbar_expect_tx(S_mbar, lit_bytes);
@@ -420,9 +427,23 @@ __global__ void __launch_bounds__(XC_THREADS, 1) k_exec_cta(const BlockDesc *__r
                     const uint32_t hi = min(lo + XC_PROWS, row_hi);
                     if (lo != row_lo) { __syncthreads(); xc_planes_reset(S, tid); __syncthreads(); }
                     uint32_t r = lo + warp;
-                    for (; r + XC_WARPS < hi && ok; r += 2 * XC_WARPS)
-                        ok = has_far ? xc_rows<true, 2>(B, r, lo << 7, has_ovl, lane) : xc_rows<false, 2>(B, r, lo << 7, has_ovl, lane);
-                    if (r < hi && ok) ok = has_far ? xc_rows<true, 1>(B, r, lo << 7, has_ovl, lane) : xc_rows<false, 1>(B, r, lo << 7, has_ovl, lane);
+                    const uint32_t variant = (has_far ? 1u : 0u) | (litg ? 2u : 0u);
+                    for (; r + XC_WARPS < hi && ok; r += 2 * XC_WARPS) {
+                        switch (variant) {
+                            case 0: ok = xc_rows<false, false, 2>(B, r, lo << 7, has_ovl, lane); break;
+                            case 1: ok = xc_rows<true, false, 2>(B, r, lo << 7, has_ovl, lane); break;
+                            case 2: ok = xc_rows<false, true, 2>(B, r, lo << 7, has_ovl, lane); break;
+                            default: ok = xc_rows<true, true, 2>(B, r, lo << 7, has_ovl, lane); break;
+                        }
+                    }
+                    if (r < hi && ok) {
+                        switch (variant) {
+                            case 0: ok = xc_rows<false, false, 1>(B, r, lo << 7, has_ovl, lane); break;
+                            case 1: ok = xc_rows<true, false, 1>(B, r, lo << 7, has_ovl, lane); break;
+                            case 2: ok = xc_rows<false, true, 1>(B, r, lo << 7, has_ovl, lane); break;
+                            default: ok = xc_rows<true, true, 1>(B, r, lo << 7, has_ovl, lane); break;
+                        }
+                    }
                 }
                 if (!ok && lane == 0) misc->bail = 2u;
                 xc_fence_proxy_async();
