@@ -3,13 +3,16 @@
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (restated port) on host cores
+    python bench.py --config c2a|c3|c4|c5                    # the other BASELINE.json configs at their full sizes
 
 A "step" is one pass of the hot path over the whole workload: config C2b = enwik9-shaped text, 8192 independent
 128 KiB single-block frames (1 GiB), level 3, checksums on.  `value` is measured with compressed frames, block
-descriptors and output all resident in HBM (kernel launches only inside the timed region); `e2e` is the same work
-through the C-ABI one-shot call with HOST buffers (host planning + H2D + kernels + D2H inside the timed region).
-Multi-GPU: frames are independent, every rank decodes its own copy of the workload (weak scaling, no data-path
-collective; NCCL only gathers the timings).
+descriptors and output all resident in HBM (kernel launches only inside the timed region, the content checksum of every
+frame included, as the reference computes it); `e2e` is the same work through the C-ABI one-shot call with HOST buffers
+(host planning + H2D + kernels + D2H inside the timed region).
+Multi-GPU: frames are independent, no data-path collective (NCCL only gathers the timings).  Both scalings are measured
+in one run: weak (every rank decodes the whole workload) and strong (the frames are sharded across the ranks,
+SURVEY 8(e)); --scaling picks which one is `value`, the other is reported under `<mode>_scaling`.
 """
 import argparse
 import json
@@ -106,94 +109,201 @@ class ClockSampler:
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def load_workload(args, rank, barrier):
+WORKLOADS = {
+    # name: (BASELINE.json config, builder(args), description)
+    "c2b": "C2b enwik9-shaped text, {n} independent {fb}-byte single-block frames, level 3, checksum on",
+    "c2a": "C2a enwik9-shaped text as {n} frame(s) of chained 128 KiB blocks (windowLog 17), level 3, checksum on",
+    "c3": "C3 {n} independent 64 KiB frames, 4-stream-Huffman-heavy literals, level 3",
+    "c4": "C4 Silesia-mix-shaped, {n} frames of 1 MiB (8 chained blocks, RLE / raw / compressed), level 3",
+    "c5": "C5 {n} small frames sharing one 110 KiB raw-content dictionary, level 3",
+}
+
+
+def build_workload(args):
     import datagen as G
-    total = args.frames * args.frame_bytes
+    c = args.config
+    if c == "c2b":
+        return G.config_c2b(total_bytes=args.frames * args.frame_bytes, frame_bytes=args.frame_bytes)
+    if c == "c2a":
+        return G.config_c2a(total_bytes=args.c2a_bytes, nframes=args.c2a_frames)
+    if c == "c3":
+        return G.config_c3(nframes=args.c3_frames)
+    if c == "c4":
+        return G.config_c4(nframes=args.c4_frames)
+    if c == "c5":
+        return G.config_c5(nframes=args.c5_frames)
+    raise SystemExit("unknown --config " + c)
+
+
+def load_workload(args, rank, barrier):
     if rank == 0:
-        fs = G.config_c2b(total_bytes=total, frame_bytes=args.frame_bytes)
+        fs = build_workload(args)   # rank 0 fills the on-disk cache, the others read it
     barrier()
     if rank != 0:
-        fs = G.config_c2b(total_bytes=total, frame_bytes=args.frame_bytes)
+        fs = build_workload(args)
     return fs
 
 
-def cpu_baseline(fs, budget_s=12.0, threads=None):
-    """The restated CPU path (oracle 'port' of ruzstd's FrameDecoder loop) on the host cores, bounded sample."""
+def workload_config(args, fs):
+    """The `config` object both arms print (same workload, same keys)."""
+    return {"workload": WORKLOADS[args.config].format(n=fs.nframes, fb=args.frame_bytes), "config": args.config,
+            "frames": fs.nframes, "D_bytes": fs.D, "C_bytes": fs.C, "ratio": fs.D / max(fs.C, 1), "sha256_plain": fs.sha256()[:16],
+            "content_checksum_computed": True,
+            "l2": "inputs larger than L2 (C+D per pass = %.0f MB vs 126 MB L2)" % ((fs.C + fs.D) / 1e6),
+            "parallelism": "frames are independent: one process per GPU, no data-path collective"}
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def bind_near_gpu(index):
+    """Pin this process (and the pinned host buffers it allocates afterwards) to the CPUs next to GPU `index`: on an 8-GPU box
+    the ranks otherwise share one socket's memory controllers and the PCIe copies of GPUs 4-7 cross the inter-socket link."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"gpu": index, "pci": bus, "cpus": len(cpus)}
+    except Exception as e:
+        return {"gpu": index, "error": str(e)[:80]}
+    return {"gpu": index, "cpus": 0}
+
+
+def cpu_decode_pass(fs, threads, buf=None):
+    """One pass of the reference's CPU path (restated port) over ALL frames of the workload, one FrameDecoder per thread."""
     from oracle import oracle as O
-    threads = threads or max(1, min(os.cpu_count() or 1, 256))
-    n = fs.nframes
-    # calibrate on a small slice, then size the sample so the run costs ~budget_s of CPU time
-    k = min(n, 64)
-    buf0 = np.zeros(int(fs.out_size[:k].sum()) + 64, dtype=np.uint8)
-    O.bulk_decode(fs.comp, fs.src_off[:k], fs.src_size[:k], fs.out_off[:k] - fs.out_off[0], fs.out_size[:k], nthreads=1, out=buf0)
+    rd = fs.raw_dict.tobytes() if fs.raw_dict is not None else None
+    if buf is None:
+        buf = np.zeros(fs.D + 64, dtype=np.uint8)   # pre-touched: page faults stay out of the timing
     t0 = time.perf_counter()
-    O.bulk_decode(fs.comp, fs.src_off[:k], fs.src_size[:k], fs.out_off[:k] - fs.out_off[0], fs.out_size[:k], nthreads=1, out=buf0)
-    per_frame = (time.perf_counter() - t0) / k
-    m = int(max(threads, min(n, budget_s / max(per_frame, 1e-9))))
-    m = min(n, m)
-    out_off = fs.out_off[:m] - fs.out_off[0]
-    buf = np.zeros(int(fs.out_size[:m].sum()) + 64, dtype=np.uint8)   # pre-touched: page faults stay out of the timing
-    O.bulk_decode(fs.comp, fs.src_off[:threads], fs.src_size[:threads], out_off[:threads], fs.out_size[:threads], nthreads=threads, out=buf)
-    t0 = time.perf_counter()
-    out, sizes = O.bulk_decode(fs.comp, fs.src_off[:m], fs.src_size[:m], out_off, fs.out_size[:m], nthreads=threads, out=buf)
-    dt = time.perf_counter() - t0
-    d = int(fs.out_size[:m].sum())
-    assert np.array_equal(out[:d], fs.plain[int(fs.out_off[0]):int(fs.out_off[0]) + d]), "CPU port output differs from the generator's plaintext"
-    one_core = float(fs.out_size[:k].sum()) / (per_frame * k) / GB
-    return {"value": d / dt / GB, "unit": "GB/s", "cores": threads, "kind": "port",
-            "sample": f"first {m} of {n} frames ({d / 2**20:.0f} MiB) of the same workload, one FrameDecoder per thread",
-            "one_core_GBps": one_core}
+    out, sizes = O.bulk_decode(fs.comp, fs.src_off, fs.src_size, fs.out_off, fs.out_size, raw_dict=rd, nthreads=threads, out=buf)
+    return time.perf_counter() - t0, out
+
+
+def libzstd_one_core(fs, budget_s=2.0):
+    """libzstd 1.5.5 (system library), one thread, on the first frames of the workload: the anchor for the reference README's
+    'ruzstd is 1.4-3.5x slower than zstd' (Readme.md:25-29)."""
+    import datagen as G
+    rd = fs.raw_dict.tobytes() if fs.raw_dict is not None else None
+    done, t0 = 0, time.perf_counter()
+    for i in range(fs.nframes):
+        f = fs.comp[int(fs.src_off[i]):int(fs.src_off[i] + fs.src_size[i])]
+        G.decompress(f, int(fs.out_size[i]), raw_dict=rd)
+        done += int(fs.out_size[i])
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return done / (time.perf_counter() - t0) / GB
+
+
+def cpu_baseline(fs, threads=None, passes=2):
+    """The restated CPU path (oracle 'port' of ruzstd's FrameDecoder loop) on the host cores: every frame of the workload,
+    all the threads this process may use."""
+    from oracle import oracle as O
+    threads = threads or host_threads()
+    k = min(fs.nframes, 64)
+    sub = fs.subset(0, k)
+    cpu_decode_pass(sub, 1)
+    one = min(cpu_decode_pass(sub, 1)[0] for _ in range(2))
+    buf = np.zeros(fs.D + 64, dtype=np.uint8)
+    cpu_decode_pass(fs, threads, buf)   # warm-up (page tables, thread stacks)
+    best, out = None, None
+    for _ in range(passes):
+        dt, out = cpu_decode_pass(fs, threads, buf)
+        best = dt if best is None else min(best, dt)
+    assert np.array_equal(out[:fs.D], fs.plain), "CPU port output differs from the generator's plaintext"
+    return {"value": fs.D / best / GB, "unit": "GB/s", "cores": threads, "kind": "port",
+            "sample": f"all {fs.nframes} frames ({fs.D / 2**20:.0f} MiB) of the same workload, one FrameDecoder per thread, best of {passes} passes after a warm-up",
+            "one_core_GBps": sub.D / one / GB, "libzstd_1.5.5_one_core_GBps": libzstd_one_core(fs)}
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (restated port; ruzstd is Rust and cannot be
-    built in this image) on the host cores, same config/metric."""
+    built in this image) on the host cores, same workload / config / metric; each step = one pass over every frame."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    class A: pass
     fs = load_workload(args, 0, lambda: None)
-    threads = max(1, min(os.cpu_count() or 1, 256))
-    from oracle import oracle as O
-    # bounded sample per step: at most 2048 frames (256 MiB)
-    m = min(fs.nframes, 2048)
-    out_off = fs.out_off[:m] - fs.out_off[0]
-    d = int(fs.out_size[:m].sum())
-    buf = np.zeros(d + 64, dtype=np.uint8)
+    threads = host_threads()
+    buf = np.zeros(fs.D + 64, dtype=np.uint8)
+    steps = max(1, args.steps if args.steps_given else 5)
+    warm = max(1, min(args.warmup, 3))
     times = []
-    for i in range(max(args.warmup, 1) + args.steps):
-        t0 = time.perf_counter()
-        O.bulk_decode(fs.comp, fs.src_off[:m], fs.src_size[:m], out_off, fs.out_size[:m], nthreads=threads, out=buf)
-        if i >= max(args.warmup, 1):
-            times.append(time.perf_counter() - t0)
+    for i in range(warm + steps):
+        dt, out = cpu_decode_pass(fs, threads, buf)
+        if i >= warm:
+            times.append(dt)
+    assert np.array_equal(out[:fs.D], fs.plain), "CPU port output differs from the generator's plaintext"
     dt = sum(times)
-    val = d * args.steps / dt / GB
-    line = {"impl": "reference", "metric": "decompressed_GBps", "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"C2b enwik9-shaped text, {fs.nframes} independent {args.frame_bytes}-byte single-block frames, level 3, checksum on",
-                       "frames": fs.nframes, "D_bytes": fs.D, "C_bytes": fs.C},
+    val = fs.D * steps / dt / GB
+    line = {"impl": "reference", "metric": "decompressed_GBps", "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": dt / steps * 1e3, "ms_per_step_min": min(times) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "config": workload_config(args, fs), "bit_exact": True,
             "cpu_baseline": {"value": val, "unit": "GB/s", "cores": threads, "kind": "port",
-                             "sample": f"first {m} of {fs.nframes} frames ({d / 2**20:.0f} MiB) per step, one FrameDecoder per thread"},
+                             "sample": f"all {fs.nframes} frames ({fs.D / 2**20:.0f} MiB) per step, one FrameDecoder per thread (content checksum computed, like FrameDecoder)",
+                             "libzstd_1.5.5_one_core_GBps": libzstd_one_core(fs)},
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
 
 
+def time_passes(batch, d_out, stream, steps, barrier, torch):
+    """K passes of the device-resident path, CUDA events on the library's stream, barrier + synchronize on both sides."""
+    barrier(); torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        batch.run(d_out)
+    ev1.record(stream)
+    stream.synchronize(); torch.cuda.synchronize(); barrier()
+    return ev0.elapsed_time(ev1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", default="c2b", choices=sorted(WORKLOADS), help="BASELINE.json config; c2b is the one the metric is quoted on")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = every rank decodes the whole workload; strong = the frames are sharded across ranks (SURVEY 8(e)). "
+                         "The other one is measured too and reported under its own key.")
     ap.add_argument("--frames", type=int, default=8192)
     ap.add_argument("--frame-bytes", type=int, default=131072)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--c2a-bytes", type=int, default=1 << 30)
+    ap.add_argument("--c2a-frames", type=int, default=1)
+    ap.add_argument("--c3-frames", type=int, default=10000)
+    ap.add_argument("--c4-frames", type=int, default=4096)
+    ap.add_argument("--c5-frames", type=int, default=100000)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    args.steps_given = args.steps is not None
+    if args.steps is None:
+        args.steps = 50 if args.config != "c2a" else 3   # one chained 1 GiB frame is a serial chain of 8192 blocks: seconds per pass
     if args.impl == "reference":
         return run_reference(args)
+    args.warmup = max(args.warmup, 3)
 
     import torch
     import torch.distributed as dist
@@ -203,117 +313,161 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_near_gpu(local) if world > 1 else None   # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
 
-    import _pkg
-    pkg = _pkg.load()
-    fs = load_workload(args, rank, barrier)
-    ctx = pkg.Context(local)
-    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
-    io = fs.frames_io()
-    D, Cb = fs.D, fs.C
+    def max_over_ranks(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # ---- device-resident path: plan + upload once, then kernel launches only
-    batch = pkg.Batch(ctx, fs.comp, io)
-    d_out = torch.empty(D + 64, dtype=torch.uint8, device="cuda")
-    info = batch.info()
-    for _ in range(args.warmup):
-        batch.run(d_out)
-    stream.synchronize()
-    res = batch.finish()
-    assert (res["status"] == 0).all(), res[res["status"] != 0][:3]
-    got = d_out[:D].cpu().numpy()
-    bit_exact = bool(np.array_equal(got, fs.plain))
-    assert bit_exact, "GPU output differs from the generator's plaintext"
-    del got
-
-    sampler = ClockSampler(local)
-    sampler.start()
-    t_wait = time.time()
-    while not sampler.rows and time.time() - t_wait < 5.0:   # nvidia-smi needs a moment before its first sample
-        batch.run(d_out); stream.synchronize()
-    sampler.rows.clear()
-    launches0 = ctx.kernel_launches()
-    barrier(); torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(args.steps):
-        batch.run(d_out)
-    ev1.record(stream)
-    stream.synchronize(); torch.cuda.synchronize(); barrier()
-    clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
-    launches = ctx.kernel_launches() - launches0
-    res = batch.finish()
-    assert (res["status"] == 0).all(), "a frame failed inside the timed region: %r" % (res[res["status"] != 0][:3],)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    ms_per_rank = [ms / args.steps]
-    if world > 1:
+    def all_ranks(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        if world == 1:
+            return [float(x)]
         allt = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(allt, t)
-        ms_per_rank = [float(x.item()) / args.steps for x in allt]
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    ms_per_step = ms_max / args.steps
-    value = D * world / (ms_per_step * 1e-3) / GB
+        return [float(v.item()) for v in allt]
+
+    import _pkg
+    pkg = _pkg.load()
+    from importlib import import_module
+    sharding = import_module("zstd_rs_b200.sharding")
+    fs_all = load_workload(args, rank, barrier)
+    ctx = pkg.Context(local)
+    ctx.set_flags(pkg.binding.FLAG_CHECKSUM)   # the reference hashes every frame it drains (decode_buffer.rs:225-226): so does the timed pass
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    dic = pkg.Dictionary.raw_content(ctx, 1, fs_all.raw_dict.tobytes()) if fs_all.raw_dict is not None else None
+
+    def measure(fs, label):
+        """device-resident passes + end-to-end calls on frame set `fs` of this rank"""
+        io = fs.frames_io()
+        D = fs.D
+        batch = pkg.Batch(ctx, fs.comp, io, forced_dict=dic)
+        d_out = torch.empty(D + 64, dtype=torch.uint8, device="cuda")
+        for _ in range(args.warmup):
+            batch.run(d_out)
+        stream.synchronize()
+        res = batch.finish()
+        assert (res["status"] == 0).all(), (label, res[res["status"] != 0][:3])
+        assert (res["calculated_checksum"] == res["checksum_from_data"])[res["has_checksum"] == 1].all(), "content checksum mismatch"
+        got = d_out[:D].cpu().numpy()
+        bit_exact = bool(np.array_equal(got, fs.plain))
+        assert bit_exact, label + ": GPU output differs from the generator's plaintext"
+        del got
+        sampler = ClockSampler(local)
+        sampler.start()
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 5.0:   # the sampler needs a moment before its first sample
+            batch.run(d_out); stream.synchronize()
+        sampler.rows.clear()
+        launches0 = ctx.kernel_launches()
+        ms = time_passes(batch, d_out, stream, args.steps, barrier, torch)
+        clocks = sampler.stop()
+        launches = ctx.kernel_launches() - launches0
+        res = batch.finish()
+        assert (res["status"] == 0).all(), "a frame failed inside the timed region: %r" % (res[res["status"] != 0][:3],)
+        out = {"fs": fs, "batch": batch, "d_out": d_out, "bit_exact": bit_exact, "ms": ms, "launches": launches, "clocks": clocks, "info": batch.info(),
+               "sched": batch.debug_sched()}
+        # the same passes without the checksum stage (what round 1 timed)
+        ctx.set_flags(0)
+        batch.run(d_out); stream.synchronize()
+        out["ms_nochk"] = time_passes(batch, d_out, stream, max(3, args.steps // 5), barrier, torch) / max(3, args.steps // 5)
+        ctx.set_flags(pkg.binding.FLAG_CHECKSUM)
+        return out
+
+    def measure_e2e(fs):
+        """the public one-shot call with pinned HOST buffers: plan + H2D + kernels + D2H inside the timed region"""
+        if args.e2e_steps <= 0:
+            return float("nan")
+        h_in = torch.from_numpy(np.ascontiguousarray(fs.comp)).pin_memory()
+        h_out = torch.empty(fs.D + 64, dtype=torch.uint8).pin_memory()
+        io = fs.frames_io()
+        ts = []
+        for i in range(1 + args.e2e_steps):
+            barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = pkg.decode_frames(ctx, h_in, io, h_out, forced_dict=dic)
+            dt = (time.perf_counter() - t0) * 1e3
+            assert (r["status"] == 0).all()
+            if i > 0:
+                ts.append(dt)
+        assert np.array_equal(h_out[:fs.D].numpy(), fs.plain), "e2e output differs"
+        return float(np.mean(ts))
+
+    # ---- weak: every rank decodes the whole workload.  strong: contiguous shards balanced by compressed bytes (sharding.py)
+    lo, hi = sharding.shard_frames(fs_all.src_size, world, rank) if world > 1 else (0, fs_all.nframes)
+    fs_shard = fs_all.subset(lo, hi) if world > 1 else fs_all
+    runs = {}
+    order = ["weak", "strong"] if world > 1 else ["weak"]
+    for mode in order:
+        fs = fs_all if mode == "weak" else fs_shard
+        m = measure(fs, mode)
+        m["ms_max"] = max_over_ranks(m["ms"])
+        m["ms_per_rank"] = [x / args.steps for x in all_ranks(m["ms"])]
+        m["e2e_ms"] = max_over_ranks(measure_e2e(fs))
+        m["D_total"] = fs_all.D * world if mode == "weak" else fs_all.D
+        m["C_total"] = fs_all.C * world if mode == "weak" else fs_all.C
+        runs[mode] = m
+        if mode != order[-1]:
+            m["batch"].close(); m["d_out"] = None
+    main_mode = args.scaling if world > 1 else "weak"
+    M = runs[main_mode]
+    fs, batch, d_out = M["fs"], M["batch"], M["d_out"]
+    ms_per_step = M["ms_max"] / args.steps
+    value = M["D_total"] / (ms_per_step * 1e-3) / GB
 
     # ---- per-kernel durations, live (CUDA events between the kernels on the launching stream)
+    if d_out is None:
+        d_out = torch.empty(fs.D + 64, dtype=torch.uint8, device="cuda")
     prof = [batch.run_profile(d_out) for _ in range(5)]
     kern_ms = {k: float(np.median([p[k] for p in prof])) for k in prof[0]}
     tot = sum(kern_ms.values())
-    timeline = {k: v for k, v in batch.run_timeline(d_out).items() if v >= 0}   # k_fse runs underneath k_exec: not separately observable
+    timeline = {k: v for k, v in batch.run_timeline(d_out).items() if v >= 0}
     dominant = max(kern_ms, key=kern_ms.get)
-
-    # ---- end to end through the C ABI with host (pinned) buffers
-    h_in = torch.from_numpy(fs.comp.copy()).pin_memory()
-    h_out = torch.empty(D + 64, dtype=torch.uint8).pin_memory()
-    e2e_ms = []
-    for i in range((1 + args.e2e_steps) if args.e2e_steps > 0 else 0):
-        barrier(); torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        r = pkg.decode_frames(ctx, h_in, io, h_out)
-        dt = (time.perf_counter() - t0) * 1e3
-        assert (r["status"] == 0).all()
-        if i > 0:
-            e2e_ms.append(dt)
-    if e2e_ms:
-        assert np.array_equal(h_out[:D].numpy(), fs.plain), "e2e output differs"
-    te = torch.tensor([float(np.mean(e2e_ms)) if e2e_ms else float("nan")], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = D * world / (float(te.item()) * 1e-3) / GB
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        achieved = (Cb + D) / (ms_per_step * 1e-3) / GB if world == 1 else (Cb + D) / (ms / args.steps * 1e-3) / GB
+        # roofline of THIS rank's pass (per-GPU quantity): algorithmic bytes of the rank's frames over the rank's pass time
+        achieved = (fs.C + fs.D) / (M["ms"] / args.steps * 1e-3) / GB
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("pipeline_dram_bytes_per_step")
         except Exception:
             pass
+        cfg = workload_config(args, fs_all)   # identical in both arms
+        run = {"frames_per_gpu": fs.nframes, "D_bytes_per_gpu": fs.D, "C_bytes_per_gpu": fs.C, "blocks_per_gpu": M["info"]["blocks"],
+               "sequences_per_gpu": M["info"]["sequences"],
+               "ranks": (f"{world} ranks, every rank decodes the whole workload" if main_mode == "weak" else f"{world} ranks, frames sharded contiguously by compressed bytes"),
+               "exec_kernels": M["sched"]}
         line = {
             "metric": "decompressed_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "ms_per_step_per_rank": ms_per_rank, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"C2b enwik9-shaped text, {fs.nframes} independent {args.frame_bytes}-byte single-block frames per GPU, level 3, checksum on",
-                       "frames_per_gpu": fs.nframes, "D_bytes_per_gpu": D, "C_bytes_per_gpu": Cb, "ratio": D / Cb,
-                       "blocks": info["blocks"], "sequences": info["sequences"],
-                       "l2": "inputs larger than L2 (C+D per step = %.0f MB vs 126 MB L2)" % ((Cb + D) / 1e6),
-                       "parallelism": f"frames sharded per rank x{world}, no data-path collective", "sha256_plain": fs.sha256()[:16]},
-            "bit_exact": bit_exact,
-            "gpu_launches": int(launches),
-            "clocks": clocks,
+            "ms_per_step": ms_per_step, "ms_per_step_per_rank": M["ms_per_rank"], "higher_is_better": True, "scaling": main_mode, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": cfg, "run": run,
+            "bit_exact": M["bit_exact"],
+            "gpu_launches": int(M["launches"]),
+            "clocks": M["clocks"],
+            "value_without_checksum_stage": M["D_total"] / (max_over_ranks(M["ms_nochk"]) * 1e-3) / GB if world == 1 else None,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "algorithmic_bytes_per_step": Cb + D,
-                         "kernel": "whole pass (k_setup + k_huf + k_fse + k_exec), CUDA events over the timed region on the library stream",
-                         "dominant_kernel": dominant, "kernel_ms": kern_ms, "overlapped_completion_ms": timeline, "kernel_share": {k: v / tot for k, v in kern_ms.items()},
-                         "read_only_GBps": Cb / (ms_per_step * 1e-3) / GB},
-            "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": int(Cb), "d2h_bytes_per_step": int(D), "ms_per_step": float(te.item()),
-                    "call": "b200z_decode_frames_batch with pinned host input/output"},
+                         "peak_source": peak_src, "algorithmic_bytes_per_step": fs.C + fs.D,
+                         "kernel": "whole pass (k_setup, k_huf || k_fse, k_exec_cta / k_exec, k_xxh64), CUDA events over the timed region on the library stream",
+                         "dominant_kernel": dominant, "kernel_ms": kern_ms, "completion_ms": timeline, "kernel_share": {k: v / tot for k, v in kern_ms.items()},
+                         "read_only_GBps": fs.C / (M["ms"] / args.steps * 1e-3) / GB},
+            "e2e": {"value": M["D_total"] / (M["e2e_ms"] * 1e-3) / GB, "unit": "GB/s", "h2d_bytes_per_step": int(fs.C), "d2h_bytes_per_step": int(fs.D), "ms_per_step": M["e2e_ms"],
+                    "steps": args.e2e_steps, "call": "b200z_decode_frames_batch with pinned host input/output"},
         }
+        for mode, m in runs.items():
+            if mode != main_mode:
+                line[mode + "_scaling"] = {"value": m["D_total"] / (m["ms_max"] / args.steps * 1e-3) / GB, "unit": "GB/s", "ms_per_step": m["ms_max"] / args.steps,
+                                           "ms_per_step_per_rank": m["ms_per_rank"], "frames_per_gpu": m["fs"].nframes, "bit_exact": m["bit_exact"],
+                                           "e2e": {"value": m["D_total"] / (m["e2e_ms"] * 1e-3) / GB, "unit": "GB/s", "ms_per_step": m["e2e_ms"]}}
+        if numa is not None:
+            line["cpu_affinity"] = numa
         if not args.skip_cpu and world == 1:   # the CPU baseline is a single-GPU-run companion (rank 0, N = 1 only)
-            line["cpu_baseline"] = cpu_baseline(fs)
+            line["cpu_baseline"] = cpu_baseline(fs_all)
         print(json.dumps(line))
     barrier()
     if world > 1:

@@ -251,6 +251,16 @@ class FrameSet:
     def sha256(self):
         return hashlib.sha256(self.plain.tobytes()).hexdigest()
 
+    def subset(self, lo, hi):
+        """Frames [lo, hi) as their own FrameSet: compressed bytes and plaintext re-based to offset 0 (views, no copies)."""
+        if lo >= hi:
+            z = np.zeros(0, dtype=np.uint64)
+            return FrameSet(self.comp[:0], z, z, z, z, self.plain[:0], self.raw_dict, self.name)
+        c0, c1 = int(self.src_off[lo]), int(self.src_off[hi - 1] + self.src_size[hi - 1])
+        p0, p1 = int(self.out_off[lo]), int(self.out_off[hi - 1] + self.out_size[hi - 1])
+        return FrameSet(self.comp[c0:c1], self.src_off[lo:hi] - np.uint64(c0), self.src_size[lo:hi], self.out_off[lo:hi] - np.uint64(p0), self.out_size[lo:hi],
+                        self.plain[p0:p1], self.raw_dict, self.name)
+
 
 def _compress_many(pieces, threads, **kw):
     with ThreadPoolExecutor(max_workers=threads) as ex:

@@ -257,6 +257,9 @@ int b200z_batch_debug_sequences(b200z_batch *b, uint32_t block, uint32_t *host_o
  * (sequence_execution.rs:59-118), symbolic where they depend on the repeat-offset history at the block's start:
  * tag << 30 | decrements, tag 1..3 = history slot + 1 */
 int b200z_batch_debug_block_flags(b200z_batch *b, uint32_t block, uint32_t *flags);
+/* execution scheduling counters of the last run (tests / profiling): [0] frames given to k_exec_cta (block assembled in
+ * shared memory), [1] frames it handed back to k_exec (one warp per frame), [2] OR of the reasons, [3] blocks handed back */
+int b200z_batch_debug_sched(b200z_batch *b, uint32_t out[4]);
 void b200z_batch_destroy(b200z_batch *b);
 
 /* ------------------------------------------------------------------------------------------------------------

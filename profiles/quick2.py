@@ -61,7 +61,7 @@ for name in (sys.argv[1:] or ["c2b"]):
         tl = b.run_timeline(d_out)
         info = b.info()
         r = {"bit_exact": ok, "frames": fs.nframes, "blocks": info["blocks"], "C": fs.C, "D": fs.D, "ms": ms, "decompressed_GBps": fs.D / ms / 1e6,
-             "frac_of_6567": (fs.C + fs.D) / ms / 1e6 / 6567.7, "kernel_ms": prof, "timeline_ms": tl, "gen_s": gen_s}
+             "frac_of_6567": (fs.C + fs.D) / ms / 1e6 / 6567.7, "kernel_ms": prof, "timeline_ms": tl, "sched": b.debug_sched(), "gen_s": gen_s}
         out[name + ":" + mode] = r
         print(name, mode, json.dumps(r), flush=True)
         b.close()

@@ -100,6 +100,7 @@ def lib():
         "b200z_batch_debug_literals": (C.c_int, [vp, C.c_uint32, vp, sz, C.POINTER(sz)]),
         "b200z_batch_debug_sequences": (C.c_int, [vp, C.c_uint32, vp, sz, C.POINTER(sz)]),
         "b200z_batch_debug_block_flags": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_uint32)]),
+        "b200z_batch_debug_sched": (C.c_int, [vp, C.POINTER(C.c_uint32)]),
         "b200z_batch_destroy": (None, [vp]),
         "b200z_frame_decoder_new": (C.c_int, [vp, pp]),
         "b200z_frame_decoder_free": (None, [vp]),
@@ -349,6 +350,11 @@ class Batch:
         n = C.c_size_t()
         self.ctx._chk(self.ctx.L.b200z_batch_debug_sequences(self.h, block, buf.ctypes.data, cap, C.byref(n)))
         return buf[:n.value].copy()
+
+    def debug_sched(self):
+        a = (C.c_uint32 * 4)()
+        self.ctx._chk(self.ctx.L.b200z_batch_debug_sched(self.h, a))
+        return {"cta_frames": a[0], "handed_back_frames": a[1], "reasons": a[2], "handed_back_blocks": a[3]}
 
     def debug_block_flags(self, block):
         v = C.c_uint32()

@@ -669,6 +669,20 @@ extern "C" int b200z_batch_debug_block_flags(b200z_batch *b, uint32_t block, uin
     *flags = ax.flags;
     return 0;
 }
+// execution scheduling counters of the LAST run: [0] frames given to k_exec_cta, [1] frames it handed back to k_exec,
+// [2] OR of the reasons (1 error status, 2 capacity, 4 raw/wide sequence records, 8 block size, 16 RLE literals that do not
+// fit, 32 sequence validation (dictionary reach, invalid offsets), 64 internal wait timed out, 128 frame state), [3] blocks left to k_exec
+extern "C" int b200z_batch_debug_sched(b200z_batch *b, uint32_t out[4]) {
+    if (!b || !out) return B200Z_ERR_INVALID_ARGUMENT;
+    b200z_ctx *c = b->ctx;
+    out[0] = (uint32_t)b->sub.cta_frames.size(); out[1] = out[2] = out[3] = 0;
+    if (!b->sub.d_sched.p) return 0;
+    CU(c, cudaStreamSynchronize(c->stream));
+    uint32_t h[4];
+    CU(c, cudaMemcpy(h, b->sub.d_sched.p, sizeof h, cudaMemcpyDeviceToHost));
+    out[1] = h[1]; out[2] = h[2]; out[3] = h[3];
+    return 0;
+}
 extern "C" void b200z_batch_destroy(b200z_batch *b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);

@@ -333,17 +333,18 @@ __global__ void __launch_bounds__(XC_THREADS, 1) k_exec_cta(const BlockDesc *__r
         uint32_t blocks_done = fs.blocks_done;
         const uint32_t nblocks = fd.nblocks;
         bool bailed = fs.status != 0 || fd.dict != nullptr;
+        uint32_t why = bailed ? 128u : 0u;   // debug: why the frame was handed to k_exec (ticket[2] collects the OR, ticket[1] the count)
         bool fresh = true;   // no block of this frame has been stored by this CTA yet
         uint32_t bi = 0;
         for (; bi < nblocks && !bailed; bi++) {
             const uint32_t b = fd.first_block + bi;
             const BlockDesc &d = descs[b];
             const BlockAux &ax = aux[b];
-            if (d.host_status || ax.status) { bailed = true; break; }
+            if (d.host_status || ax.status) { bailed = true; why |= 1u; break; }
             const uint32_t btype = d.btype;
             if (btype != BT_COMPRESSED) {
                 const uint32_t n = d.raw_size;
-                if (produced + n > cap) { bailed = true; break; }
+                if (produced + n > cap) { bailed = true; why |= 2u; break; }
                 uint8_t *dst = out + produced;
                 if (btype == BT_RAW) { const uint8_t *srcp = input + d.src_off; for (uint32_t j = tid; j < n; j += XC_THREADS) dst[j] = srcp[j]; }
                 else { const uint8_t v = input[d.src_off]; for (uint32_t j = tid; j < n; j += XC_THREADS) dst[j] = v; }
@@ -354,10 +355,10 @@ __global__ void __launch_bounds__(XC_THREADS, 1) k_exec_cta(const BlockDesc *__r
                 continue;
             }
             const uint32_t nseq = d.nseq;
-            if (nseq && (ax.pad || (ax.flags & (AUX_RAW_OFFSETS | AUX_WIDE)))) { bailed = true; break; }
+            if (nseq && (ax.pad || (ax.flags & (AUX_RAW_OFFSETS | AUX_WIDE)))) { bailed = true; why |= ax.pad ? 1u : 4u; break; }
             const uint32_t out_size = ax.out_size, regen = d.regen_size;
             const uint32_t sum_ll = nseq ? ax.sum_ll : 0u;
-            if (out_size > XC_WIN_MAX || produced + out_size > cap || sum_ll > regen || regen > out_size) { bailed = true; break; }
+            if (out_size > XC_WIN_MAX || produced + out_size > cap || sum_ll > regen || regen > out_size) { bailed = true; why |= produced + out_size > cap ? 2u : 8u; break; }
             if (out_size == 0) { blocks_done++; continue; }
             XcBlk B;
             B.S = S;
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(XC_THREADS, 1) k_exec_cta(const BlockDesc *__r
             const uint32_t lit_bytes = (loff + regen + 15u) & ~15u;
             // literals that do not fit beside the window are read from global memory byte by byte (a block that is nearly all literals)
             const bool litg = wbytes + lit_bytes > XC_DATA_BYTES;
-            if (litg && lt == LT_RLE) { bailed = true; break; }
+            if (litg && lt == LT_RLE) { bailed = true; why |= 16u; break; }
             B.lit_gp = litg ? lit_g + loff : nullptr;
             B.lit_s = wbytes + loff;
             const bool has_far = B.reach != 0;
@@ -465,7 +466,7 @@ __global__ void __launch_bounds__(XC_THREADS, 1) k_exec_cta(const BlockDesc *__r
                 }
                 blk_bail = misc->bail != 0;
             }
-            if (blk_bail) { bailed = true; break; }
+            if (blk_bail) { bailed = true; why |= misc->bail == 2u ? 64u : 32u; break; }
             // ---- head / tail bytes around the 16-byte aligned part
             {
                 const uint32_t head_end = min((B.woff + 15u) & ~15u, B.a_end);
@@ -491,6 +492,7 @@ __global__ void __launch_bounds__(XC_THREADS, 1) k_exec_cta(const BlockDesc *__r
             }
             // what is left for k_exec: the rest of the frame from block `bi`, or only the frame-level epilogue, or nothing
             resume[f] = bailed ? bi : (fd.host_status ? nblocks : nblocks + 1u);
+            if (bailed) { atomicAdd(ticket + 1, 1u); atomicOr(ticket + 2, why); atomicAdd(ticket + 3, nblocks - bi); }
         }
     }
     if (tid == 0) xc_bulk_wait0();
