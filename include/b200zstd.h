@@ -240,9 +240,9 @@ int b200z_batch_finish(b200z_batch *b, b200z_frame_result *results);
 /* b200z_batch_run with a CUDA event between kernels: synchronises and returns each kernel's device milliseconds
  * (stage_ms[i] for kernel b200z_stage_kernel_name(i), i < b200z_num_stages()).  Profiling aid for bench.py. */
 int b200z_batch_run_profile(b200z_batch *b, uint8_t *d_output, size_t output_cap, float *stage_ms, size_t nstages);
-/* one overlapped pass exactly as b200z_batch_run launches it, with an event after k_setup, k_huf and k_exec:
- * out_ms[0], [1], [3] = their completion times relative to the start of the pass; out_ms[2] = -1 (k_fse runs underneath
- * k_exec, which is launched as its programmatic dependent: an event between the two would serialise them) (n >= 4) */
+/* one pass exactly as b200z_batch_run launches it (k_huf on a side stream beside k_fse), with events on the main stream:
+ * out_ms[0..3] = completion time, relative to the start of the pass, of k_setup, of the entropy pair, of k_exec_cta and of
+ * k_exec (n >= 4) */
 int b200z_batch_run_timeline(b200z_batch *b, uint8_t *d_output, size_t output_cap, float *out_ms, size_t n);
 int b200z_num_stages(void);
 const char *b200z_stage_kernel_name(int stage);
@@ -261,6 +261,57 @@ int b200z_batch_debug_block_flags(b200z_batch *b, uint32_t block, uint32_t *flag
  * shared memory), [1] frames it handed back to k_exec (one warp per frame), [2] OR of the reasons, [3] blocks handed back */
 int b200z_batch_debug_sched(b200z_batch *b, uint32_t out[4]);
 void b200z_batch_destroy(b200z_batch *b);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Tier 1b -- block-level batch entry: the thin FFI for a host that keeps the reference's OWN frame / block /
+ * section header parsing (frame.rs:6-85, block_decoder.rs:201-247, literals_section.rs:117-223,
+ * sequence_section.rs:108-167) and ships compressed blocks.  It replaces the one call site of the hot path,
+ * BlockDecoder::decompress_block (block_decoder.rs:97-197, called at :140-145 / :176-183), for many blocks of many
+ * frames at once.  A descriptor carries what decompress_block has in hand when it calls decode_literals /
+ * decode_sequences / execute_sequences.  The entropy tables are built on the GPU from the descriptions inside the
+ * block content, so the "table pool" is implicit: Repeat / Treeless modes refer to the tables of the previous block
+ * of the same frame (blocks of a frame are consecutive and in order), or to the frame's dictionary.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct b200z_block_desc {
+    uint64_t src_off;             /* offset of the block CONTENT (after the 3-byte header) in `compressed`            */
+    uint32_t content_size;        /* BlockHeader::content_size (block.rs:31-43)                                        */
+    uint32_t block_type;          /* 0 Raw, 1 RLE, 2 Compressed                                                        */
+    uint32_t decompressed_size;   /* BlockHeader::decompressed_size (Raw / RLE blocks)                                 */
+    uint32_t last_block;
+    /* what LiteralsSection::parse_from_header gave (literals_section.rs:9-28); checked against the content */
+    uint32_t literals_type;       /* 0 Raw, 1 RLE, 2 Compressed, 3 Treeless                                            */
+    uint32_t regenerated_size;
+    uint32_t compressed_size;     /* 0 for Raw / RLE literals                                                          */
+    uint32_t num_streams;         /* 1 or 4 (Compressed / Treeless), else 0                                            */
+    /* what SequencesHeader::parse_from_header gave (sequence_section.rs:10-19) */
+    uint32_t num_sequences;
+    uint32_t modes;               /* the compression-modes byte (0 when num_sequences == 0)                            */
+} b200z_block_desc;
+
+typedef struct b200z_block_frame {
+    uint64_t out_off;             /* where the frame's byte 0 goes inside `output`                                     */
+    uint64_t out_cap;
+    uint64_t window_size;         /* FrameHeader::window_size (frame.rs:116)                                           */
+    const b200z_dict *dict;       /* dictionary in use (initial tables, offset history, content) or NULL               */
+    uint32_t first_block;         /* index of the frame's first descriptor                                             */
+    uint32_t num_blocks;
+} b200z_block_frame;
+
+typedef struct b200z_block_status {
+    int32_t status;               /* 0, a b200z_error, or B200Z_BLOCK_NOT_REACHED (an earlier block of the frame failed) */
+    int32_t stage;
+    uint32_t out_size;            /* bytes this block added to the frame's output                                      */
+    uint32_t reserved;
+} b200z_block_status;
+#define B200Z_BLOCK_NOT_REACHED (-1)
+
+/* Decodes `nblocks` blocks of `nframes` frames.  `compressed` / `output` are host or device memory (B200Z_MEM_*).
+ * Returns 0 when the submission ran; per-block outcomes in status[nblocks], per-frame totals in frame_out_size[nframes]
+ * (either may be NULL).  B200Z_ERR_INVALID_ARGUMENT when a descriptor disagrees with the section headers found in the
+ * block content. */
+int b200z_decode_blocks_batch(b200z_ctx *ctx, const b200z_block_desc *blocks, size_t nblocks, const b200z_block_frame *frames,
+                              size_t nframes, const uint8_t *compressed, size_t compressed_len, int compressed_mem, uint8_t *output,
+                              size_t output_cap, int output_mem, b200z_block_status *status, uint64_t *frame_out_size);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Tier 2 -- mirror of ruzstd's FrameDecoder (decoding/frame_decoder.rs:154-627), GPU-backed.

@@ -546,3 +546,57 @@ def test_exec_run_shapes(pkg, ctx, oracle, exec_mode):
         assert got == p, f"piece {i}: GPU output differs from the plaintext"
         assert oracle.decode_frame(bytes(frames[i]))[0] == p
     assert (out[oo:] == 0).all()
+
+
+def test_block_level_entry(pkg, ctx, oracle, manifest, exec_mode):
+    """b200z_decode_blocks_batch: the thin FFI for a host that keeps the reference's own header parsing (replaces the call site
+    BlockDecoder::decompress_block, block_decoder.rs:97-197).  Descriptors come from tests/refwalk.py (a restatement of the
+    reference's header parsers); per-block output sizes are checked against the oracle's block trace, bytes against the corpus."""
+    import refwalk
+    B = pkg.binding
+    names = sorted(manifest["corpus"])[:40]
+    frames = [read_golden("decodecorpus", n) for n in names]
+    sizes = [manifest["corpus"][n]["size"] for n in names]
+    offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+    comp, blocks, fr = refwalk.walk(frames, offs, sizes, (B.BLOCK_DESC_DTYPE, B.BLOCK_FRAME_DTYPE))
+    out = np.zeros(int(sum(sizes)) + 16, dtype=np.uint8)
+    st, fo = pkg.decode_blocks(ctx, blocks, fr, comp, out)
+    assert (st["status"] == 0).all(), st[st["status"] != 0][:3]
+    nb = 0
+    for i, n in enumerate(names):
+        assert fo[i] == sizes[i], n
+        got = out[offs[i]:offs[i] + sizes[i]].tobytes()
+        assert hashlib.sha256(got).hexdigest() == manifest["corpus"][n]["sha256"], n
+        d = oracle.FrameDecoder(); d.trace_enable()
+        r = d.reset(frames[i]); d.decode_blocks(r); d.collect()
+        tblocks, _, _ = d.trace()
+        assert len(tblocks) == fr[i]["num_blocks"]
+        for k, tb in enumerate(tblocks):
+            b = blocks[fr[i]["first_block"] + k]
+            assert st[fr[i]["first_block"] + k]["out_size"] == tb["out_size"], (n, k)
+            if tb["block_type"] == 2:
+                assert (b["literals_type"], b["regenerated_size"], b["num_sequences"]) == (tb["literals_type"], tb["regenerated_size"], tb["num_sequences"])
+            nb += 1
+    assert nb > 300
+    # device-resident input and output
+    import torch
+    d_in = torch.from_numpy(comp.copy()).cuda()
+    d_out = torch.zeros(len(out), dtype=torch.uint8, device="cuda")
+    st2, fo2 = pkg.decode_blocks(ctx, blocks, fr, d_in, d_out)
+    assert (st2["status"] == 0).all() and np.array_equal(d_out.cpu().numpy()[:sum(sizes)], out[:sum(sizes)])
+    # a corrupted block fails alone: its frame stops there, later blocks are "not reached", other frames are untouched
+    bad = comp.copy()
+    victim = next(j for j in range(len(blocks)) if blocks[j]["block_type"] == 2 and blocks[j]["num_sequences"] > 8 and not blocks[j]["last_block"])
+    bad[int(blocks[victim]["src_off"]) + int(blocks[victim]["content_size"]) - 1] = 0   # sequence bitstream without its padding marker
+    st3, fo3 = pkg.decode_blocks(ctx, blocks, fr, bad, np.zeros_like(out))
+    fidx = next(i for i in range(len(fr)) if fr[i]["first_block"] <= victim < fr[i]["first_block"] + fr[i]["num_blocks"])
+    assert st3[victim]["status"] > 0
+    lo, hi = fr[fidx]["first_block"], fr[fidx]["first_block"] + fr[fidx]["num_blocks"]
+    assert (st3[lo:victim]["status"] == 0).all() and (st3[victim + 1:hi]["status"] == B.BLOCK_NOT_REACHED).all()
+    others = np.ones(len(st3), bool); others[lo:hi] = False
+    assert (st3[others]["status"] == 0).all()
+    # a descriptor that disagrees with the block content is rejected
+    wrong = blocks.copy()
+    wrong[victim]["num_sequences"] += 1
+    with pytest.raises(pkg.B200ZError):
+        pkg.decode_blocks(ctx, wrong, fr, comp, np.zeros_like(out))

@@ -9,6 +9,6 @@ Import name: ``zstd_rs_b200`` (the directory name has a hyphen; see ``_pkg.py`` 
 """
 from .binding import (  # noqa: F401
     ALL, UPTO_BLOCKS, UPTO_BYTES, B200ZError, Batch, Context, Dictionary, FrameDecoder, StreamingDecoder,
-    build, decode_frames, error_names, lib, lib_path, xxh64,
+    build, decode_blocks, decode_frames, error_names, lib, lib_path, xxh64,
 )
 from . import binding  # noqa: F401

@@ -40,6 +40,12 @@ class FrameResult(C.Structure):
 
 
 FRAME_IO_DTYPE = np.dtype([("src_off", "<u8"), ("src_size", "<u8"), ("out_off", "<u8"), ("out_cap", "<u8")])
+BLOCK_DESC_DTYPE = np.dtype([("src_off", "<u8"), ("content_size", "<u4"), ("block_type", "<u4"), ("decompressed_size", "<u4"), ("last_block", "<u4"),
+                             ("literals_type", "<u4"), ("regenerated_size", "<u4"), ("compressed_size", "<u4"), ("num_streams", "<u4"),
+                             ("num_sequences", "<u4"), ("modes", "<u4")])
+BLOCK_FRAME_DTYPE = np.dtype([("out_off", "<u8"), ("out_cap", "<u8"), ("window_size", "<u8"), ("dict", "<u8"), ("first_block", "<u4"), ("num_blocks", "<u4")])
+BLOCK_STATUS_DTYPE = np.dtype([("status", "<i4"), ("stage", "<i4"), ("out_size", "<u4"), ("reserved", "<u4")])
+BLOCK_NOT_REACHED = -1
 FRAME_RESULT_DTYPE = np.dtype([("out_size", "<u8"), ("bytes_read", "<u8"), ("content_size", "<u8"), ("window_size", "<u8"),
                                ("status", "<i4"), ("stage", "<i4"), ("blocks_decoded", "<u4"), ("error_block", "<u4"),
                                ("has_checksum", "<u4"), ("checksum_from_data", "<u4"), ("has_dict_id", "<u4"), ("dict_id", "<u4"),
@@ -89,6 +95,7 @@ def lib():
         "b200z_dict_content_size": (sz, [vp]),
         "b200z_dict_destroy": (None, [vp]),
         "b200z_decode_frames_batch": (C.c_int, [vp, vp, sz, C.c_int, vp, sz, pp, sz, vp, C.c_uint64, vp, sz, C.c_int, vp]),
+        "b200z_decode_blocks_batch": (C.c_int, [vp, vp, sz, vp, sz, vp, sz, C.c_int, vp, sz, C.c_int, vp, vp]),
         "b200z_batch_prepare": (C.c_int, [vp, vp, sz, C.c_int, vp, sz, pp, sz, vp, C.c_uint64, pp]),
         "b200z_batch_run": (C.c_int, [vp, vp, sz]),
         "b200z_batch_finish": (C.c_int, [vp, vp]),
@@ -278,6 +285,23 @@ def _dict_args(dicts, forced):
     dicts = list(dicts or [])
     arr = (C.c_void_p * max(len(dicts), 1))(*[d.h for d in dicts])
     return arr, len(dicts), (forced.h if forced is not None else None)
+
+
+def decode_blocks(ctx, blocks, frames, compressed, output):
+    """b200z_decode_blocks_batch: the block-level entry (what replaces BlockDecoder::decompress_block, block_decoder.rs:97-197).
+    blocks: BLOCK_DESC_DTYPE array, frames: BLOCK_FRAME_DTYPE array ('dict' = Dictionary or 0 per frame via `set_frame_dicts`).
+    Returns (block status array, per-frame output sizes)."""
+    blocks = np.ascontiguousarray(blocks, dtype=BLOCK_DESC_DTYPE)
+    frames = np.ascontiguousarray(frames, dtype=BLOCK_FRAME_DTYPE)
+    st = np.zeros(len(blocks), dtype=BLOCK_STATUS_DTYPE)
+    fo = np.zeros(len(frames), dtype=np.uint64)
+    ip, il, _k1 = _ptr(compressed)
+    op, ol, _k2 = _ptr(output)
+    e = ctx.L.b200z_decode_blocks_batch(ctx.h, blocks.ctypes.data, len(blocks), frames.ctypes.data, len(frames), ip, il,
+                                        MEM_DEVICE if _is_device(compressed) else MEM_HOST, op, ol, MEM_DEVICE if _is_device(output) else MEM_HOST,
+                                        st.ctypes.data, fo.ctypes.data)
+    ctx._chk(e)
+    return st, fo
 
 
 def decode_frames(ctx, input, frames, output, dicts=None, forced_dict=None, max_window_size=0):

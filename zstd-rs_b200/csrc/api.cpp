@@ -885,6 +885,115 @@ extern "C" int b200z_decode_frames_batch(b200z_ctx *c, const uint8_t *input, siz
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// tier 1b: block-level batch entry -- replaces the call site of the hot path, BlockDecoder::decompress_block
+// (block_decoder.rs:97-197), for a host that keeps the reference's own header parsing.
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int b200z_decode_blocks_batch(b200z_ctx *c, const b200z_block_desc *blocks, size_t nblocks, const b200z_block_frame *frames, size_t nframes,
+                                         const uint8_t *compressed, size_t compressed_len, int compressed_mem, uint8_t *output, size_t output_cap,
+                                         int output_mem, b200z_block_status *status, uint64_t *frame_out_size) {
+    if (!c || (!blocks && nblocks) || (!frames && nframes) || (!compressed && compressed_len) || (!output && output_cap)) return B200Z_ERR_INVALID_ARGUMENT;
+    if (int e = c->use()) return e;
+    std::vector<uint8_t> host_copy;
+    const uint8_t *hin = compressed;
+    if (compressed_mem == B200Z_MEM_DEVICE) {   // the section headers are walked on the host (as in b200z_batch_prepare)
+        host_copy.resize(compressed_len);
+        if (compressed_len) CU(c, cudaMemcpy(host_copy.data(), compressed, compressed_len, cudaMemcpyDeviceToHost));
+        hin = host_copy.data();
+    }
+    Submission s;
+    std::vector<const b200z_dict *> dlist;
+    std::vector<int64_t> sub_of(nblocks, -1);      // caller's block index -> descriptor index in the submission
+    std::vector<uint32_t> frame_first(nframes, 0);
+    for (size_t f = 0; f < nframes; f++) {
+        const b200z_block_frame &bf = frames[f];
+        if ((uint64_t)bf.first_block + bf.num_blocks > nblocks) return B200Z_ERR_INVALID_ARGUMENT;
+        int dict_idx = -1;
+        if (bf.dict) {
+            auto it = std::find(dlist.begin(), dlist.end(), bf.dict);
+            if (it == dlist.end()) { dlist.push_back(bf.dict); s.carries.push_back(carry_of_dict(bf.dict)); dict_idx = (int)dlist.size() - 1; }
+            else dict_idx = (int)(it - dlist.begin());
+        }
+        FrameDesc fd;
+        memset(&fd, 0, sizeof fd);
+        fd.out_off = bf.out_off; fd.out_cap = bf.out_cap; fd.window_size = bf.window_size;
+        fd.dict = bf.dict ? bf.dict->d_content : nullptr; fd.dict_len = bf.dict ? bf.dict->content_len : 0;
+        fd.first_block = (uint32_t)s.descs.size();
+        frame_first[f] = fd.first_block;
+        FrameState st;
+        memset(&st, 0, sizeof st);
+        st.hist[0] = bf.dict ? bf.dict->hist[0] : 1; st.hist[1] = bf.dict ? bf.dict->hist[1] : 4; st.hist[2] = bf.dict ? bf.dict->hist[2] : 8;
+        TableCursor cur;
+        if (dict_idx >= 0) cursor_from_carry(cur, s.carries[dict_idx], (uint32_t)dict_idx);
+        for (uint32_t k = 0; k < bf.num_blocks; k++) {
+            const b200z_block_desc &bd = blocks[bf.first_block + k];
+            if (bd.block_type > BT_COMPRESSED || bd.src_off > compressed_len || bd.content_size > compressed_len - bd.src_off) return B200Z_ERR_INVALID_ARGUMENT;
+            BlockDesc d;
+            memset(&d, 0, sizeof d);
+            BlockRefs r;
+            d.src_off = bd.src_off; d.src_size = bd.content_size; d.frame = (uint32_t)f; d.btype = bd.block_type; d.raw_size = bd.decompressed_size;
+            d.block_in_frame = k; d.last = bd.last_block;
+            if (bd.block_type == BT_COMPRESSED) {
+                plan_compressed_block(hin + bd.src_off, bd.content_size, d, r, cur, s.n_huf, s.n_fse, s.lit_bytes, s.nseq);
+                // the descriptor says what the caller's parsers found: it must be what the content says
+                const bool lit_seen = !(d.host_status && (d.host_status >> 24) == 1 && d.lit_type == 0 && d.regen_size == 0 && d.lit_off == 0);
+                if (lit_seen && (d.lit_type != bd.literals_type || d.regen_size != bd.regenerated_size)) return B200Z_ERR_INVALID_ARGUMENT;
+                if (!d.host_status && (d.nseq != bd.num_sequences || (d.nseq && d.modes != bd.modes))) return B200Z_ERR_INVALID_ARGUMENT;
+            } else if (bd.block_type == BT_RAW ? bd.content_size != bd.decompressed_size : bd.content_size != 1) return B200Z_ERR_INVALID_ARGUMENT;
+            sub_of[bf.first_block + k] = (int64_t)s.descs.size();
+            s.descs.push_back(d); s.refs.push_back(r);
+            if (d.host_status) break;   // decompress_block would have returned here: later blocks of the frame are never reached
+        }
+        fd.nblocks = (uint32_t)s.descs.size() - fd.first_block;
+        s.frames.push_back(fd); s.states.push_back(st);
+    }
+    DevBuf d_in_own, d_out_own;
+    const uint8_t *d_in = compressed;
+    if (compressed_mem != B200Z_MEM_DEVICE) {
+        if (int e = d_in_own.ensure(compressed_len + 16, false)) return e;
+        if (compressed_len) CU(c, cudaMemcpyAsync(d_in_own.p, compressed, compressed_len, cudaMemcpyHostToDevice, c->stream));
+        d_in = d_in_own.as<uint8_t>();
+    }
+    uint8_t *d_out = output;
+    if (output_mem != B200Z_MEM_DEVICE) {
+        if (int e = d_out_own.ensure(output_cap + 16, false)) return e;
+        d_out = d_out_own.as<uint8_t>();
+    }
+    if (int e = s.upload(c)) return e;
+    PipelineArgs a = s.args(d_in, d_out, output_cap);
+    PipelineStreams ps{c->stream, c->side, c->ev_fork, c->ev_join};
+    if (int le = launch_pipeline_overlapped(a, ps)) return c->set_cuda_err((cudaError_t)le, "launch_pipeline");
+    c->launches += pipeline_launch_count(a);
+    std::vector<FrameState> st(s.states.size());
+    std::vector<BlockAux> aux(s.descs.size());
+    if (!st.empty()) CU(c, cudaMemcpyAsync(st.data(), s.d_states.p, st.size() * sizeof(FrameState), cudaMemcpyDeviceToHost, c->stream));
+    if (!aux.empty()) CU(c, cudaMemcpyAsync(aux.data(), s.d_aux.p, aux.size() * sizeof(BlockAux), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    uint64_t lo = UINT64_MAX, hi = 0;
+    for (size_t f = 0; f < nframes; f++) {
+        const b200z_block_frame &bf = frames[f];
+        const FrameState &fs = st[f];
+        if (frame_out_size) frame_out_size[f] = fs.produced;
+        if (fs.produced) { lo = std::min<uint64_t>(lo, bf.out_off); hi = std::max<uint64_t>(hi, bf.out_off + fs.produced); }
+        if (!status) continue;
+        for (uint32_t k = 0; k < bf.num_blocks; k++) {
+            b200z_block_status &o = status[bf.first_block + k];
+            memset(&o, 0, sizeof o);
+            const int64_t si = sub_of[bf.first_block + k];
+            const bool failed_here = fs.status && k == fs.error_block;
+            if (si < 0 || (fs.status && k > fs.error_block)) { o.status = B200Z_BLOCK_NOT_REACHED; continue; }
+            if (failed_here) { o.status = (int32_t)(fs.status & 0xffffu); o.stage = (int32_t)((fs.status >> 16) & 0xffu); continue; }
+            const BlockDesc &d = s.descs[(size_t)si];
+            o.out_size = d.btype == BT_COMPRESSED ? aux[(size_t)si].out_size : d.raw_size;
+        }
+    }
+    if (output_mem != B200Z_MEM_DEVICE && hi > lo) {
+        hi = std::min<uint64_t>(hi, output_cap);
+        if (hi > lo) { CU(c, cudaMemcpyAsync(output + lo, d_out + lo, hi - lo, cudaMemcpyDeviceToHost, c->stream)); CU(c, cudaStreamSynchronize(c->stream)); }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // tier 2: FrameDecoder mirror (decoding/frame_decoder.rs)
 // ---------------------------------------------------------------------------------------------------------------
 struct b200z_frame_decoder {

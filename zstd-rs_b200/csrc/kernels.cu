@@ -14,6 +14,7 @@
 // Integer/byte work only; the roofline is HBM bandwidth.
 #include <cuda_runtime.h>
 #include <limits.h>
+#include <stdlib.h>
 #include <stdint.h>
 
 #include "kernels.h"
@@ -944,10 +945,10 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                                                         const FrameDesc *__restrict__ frames, FrameState *__restrict__ states,
                                                         const uint8_t *__restrict__ input, const uint8_t *__restrict__ lit_scratch,
                                                         const uint32_t *__restrict__ seq_scratch, uint8_t *__restrict__ output, uint64_t output_cap,
-                                                        uint32_t nframes, const uint32_t *__restrict__ resume) {
+                                                        uint32_t nframes, const uint32_t *__restrict__ resume, uint32_t frame_base) {
     __shared__ uint32_t s_mask[EXEC_WARPS][EXEC_MASK_WORDS];
     __shared__ __align__(16) uint2 s_recs[EXEC_WARPS][EXEC_BATCH];
-    const uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t f = frame_base + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const uint32_t lane = threadIdx.x & 31, lt = lanemask_lt();
     if (f >= nframes) return;
     uint32_t a_mask = (uint32_t)__cvta_generic_to_shared(s_mask[threadIdx.x >> 5]);   // this warp's bitmask of sequence ends
@@ -1244,7 +1245,29 @@ __global__ void k_xxh64(const FrameDesc *__restrict__ frames, FrameState *__rest
     const uint64_t nstripes = len >> 5;
     uint64_t v = k == 0 ? P1 + P2 : (k == 1 ? P2 : (k == 2 ? 0ull : 0ull - P1));
     const uint8_t *q = p + 8 * k;
-    for (uint64_t s = 0; s < nstripes; s++, q += 32) {
+    // the accumulator is a serial chain, the loads are not: 16 stripes' words are requested together (the loop is bound by
+    // memory latency otherwise: 1 ms per GiB with one load in flight per lane)
+    uint64_t s = 0;
+    if ((((uintptr_t)q) & 7) == 0) {
+        for (; s + 16 <= nstripes; s += 16, q += 512) {
+            uint64_t w[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) w[i] = *reinterpret_cast<const uint64_t *>(q + 32 * i);
+#pragma unroll
+            for (int i = 0; i < 16; i++) { v += w[i] * P2; v = rotl64(v, 31) * P1; }
+        }
+    } else {
+        const uint32_t sh = (uint32_t)(((uintptr_t)q) & 7) * 8u;
+        const uint64_t *qa = reinterpret_cast<const uint64_t *>(((uintptr_t)q) & ~(uintptr_t)7);
+        for (; s + 16 <= nstripes; s += 16, q += 512, qa += 64) {
+            uint64_t lo[16], hi[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) { lo[i] = qa[4 * i]; hi[i] = qa[4 * i + 1]; }
+#pragma unroll
+            for (int i = 0; i < 16; i++) { const uint64_t w = (lo[i] >> sh) | (hi[i] << (64u - sh)); v += w * P2; v = rotl64(v, 31) * P1; }
+        }
+    }
+    for (; s < nstripes; s++, q += 32) {
         v += ld_u64_unaligned(q) * P2;
         v = rotl64(v, 31) * P1;
     }
@@ -1337,9 +1360,16 @@ int launch_stage(const PipelineArgs &a, int stage, cudaStream_t s) {
             break;
         case 4:
             // every other frame, and whatever k_exec_cta left (resume[]): one warp per frame
-            if (a.nframes)
-                k_exec<<<cdiv(a.nframes, EXEC_WARPS), EXEC_WARPS * 32, 0, s>>>(a.descs, a.aux, a.frames, a.states, a.input, a.lit_scratch, a.seq_scratch,
-                                                                a.output, a.output_cap, a.nframes, a.resume);
+            if (a.nframes) {
+                // optional waves (B200Z_EXEC_WAVE frames per launch): fewer live windows, so match sources stay in L2
+                static const uint32_t wave = [] { const char *e = getenv("B200Z_EXEC_WAVE"); return e ? (uint32_t)strtoul(e, nullptr, 10) : 0u; }();
+                const uint32_t step = wave ? wave : a.nframes;
+                for (uint32_t base = 0; base < a.nframes; base += step) {
+                    const uint32_t n = a.nframes - base < step ? a.nframes - base : step;
+                    k_exec<<<cdiv(n, EXEC_WARPS), EXEC_WARPS * 32, 0, s>>>(a.descs, a.aux, a.frames, a.states, a.input, a.lit_scratch, a.seq_scratch,
+                                                                 a.output, a.output_cap, base + n, a.resume, base);
+                }
+            }
             break;
         default: break;
     }
