@@ -1293,6 +1293,7 @@ __global__ void k_xxh64(const FrameDesc *__restrict__ frames, FrameState *__rest
 
 }  // namespace b200z
 
+#include "fse2.cuh"
 #include "exec_cta.cuh"
 
 namespace b200z {
@@ -1316,6 +1317,10 @@ int init_kernels() {
     cudaError_t e = cudaFuncSetAttribute(k_fse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFseSmem);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_huf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHufSmem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_fse2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFse2Smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_fse2, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_exec_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XC_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
@@ -1348,8 +1353,12 @@ int launch_stage(const PipelineArgs &a, int stage, cudaStream_t s) {
                 k_huf<<<cdiv(a.nblocks, HUF_BLOCKS_PER_CTA), 32, kHufSmem, s>>>(a.descs, a.aux, a.input, a.lit_scratch, a.nblocks);
             break;
         case 2:
-            if (a.nblocks)
-                k_fse<<<cdiv(a.nblocks, FSE_BLOCKS_PER_CTA), 32, kFseSmem, s>>>(a.descs, a.aux, a.input, a.seq_scratch, a.nblocks);
+            if (a.nblocks) {
+                // B200Z_FSE=1: round 1's single-warp kernel (kept for A/B measurements); default: chain warp + value warp
+                static const bool one_warp = [] { const char *e = getenv("B200Z_FSE"); return e && e[0] == '1'; }();
+                if (one_warp) k_fse<<<cdiv(a.nblocks, FSE_BLOCKS_PER_CTA), 32, kFseSmem, s>>>(a.descs, a.aux, a.input, a.seq_scratch, a.nblocks);
+                else k_fse2<<<cdiv(a.nblocks, F2_LANES), 64, kFse2Smem, s>>>(a.descs, a.aux, a.input, a.seq_scratch, a.nblocks);
+            }
             break;
         case 3:
             // frames whose blocks are assembled in shared memory: persistent CTAs, one per SM, frames from a ticket counter
