@@ -240,9 +240,9 @@ int b200z_batch_finish(b200z_batch *b, b200z_frame_result *results);
 /* b200z_batch_run with a CUDA event between kernels: synchronises and returns each kernel's device milliseconds
  * (stage_ms[i] for kernel b200z_stage_kernel_name(i), i < b200z_num_stages()).  Profiling aid for bench.py. */
 int b200z_batch_run_profile(b200z_batch *b, uint8_t *d_output, size_t output_cap, float *stage_ms, size_t nstages);
-/* one pass exactly as b200z_batch_run launches it (k_huf on a side stream beside k_fse), with events on the main stream:
- * out_ms[0..3] = completion time, relative to the start of the pass, of k_setup, of the entropy pair, of k_exec_cta and of
- * k_exec (n >= 4) */
+/* one pass exactly as b200z_batch_run launches it, with events on the stream: out_ms[0..3] = completion time, relative to the
+ * start of the pass, of k_setup, of k_huf, of the pair k_fse + k_exec (k_exec runs beside k_fse as its programmatic dependent)
+ * and of k_exec_cta + the k_exec launch that takes what it handed back (n >= 4) */
 int b200z_batch_run_timeline(b200z_batch *b, uint8_t *d_output, size_t output_cap, float *out_ms, size_t n);
 int b200z_num_stages(void);
 const char *b200z_stage_kernel_name(int stage);

@@ -250,6 +250,7 @@ struct Submission {
     uint64_t lit_bytes = 0, nseq = 0;
     DevBuf d_descs, d_aux, d_frames, d_states, d_huf, d_fse, d_lit, d_seq, d_sched;
     std::vector<uint32_t> cta_frames;   // frames executed by k_exec_cta (the rest: k_exec, one warp per frame)
+    std::vector<uint32_t> sched_image;  // host copy of the initial ticket / resume[] image (kept alive for the async upload)
 
     void clear() {
         descs.clear(); refs.clear(); frames.clear(); states.clear(); carries.clear();
@@ -284,7 +285,8 @@ struct Submission {
                 if (force_cta || (fd.nblocks >= 2 && src >= 4096)) cta_frames.push_back((uint32_t)f);
             }
         }
-        if ((e = d_sched.ensure(16 + 4 * (frames.size() + cta_frames.size()) + 16))) return e;
+        // scheduling buffer: [ticket + 3 counters][resume[nframes]][cta frame list][initial image of the first two parts]
+        if ((e = d_sched.ensure(2 * (16 + 4 * frames.size()) + 4 * cta_frames.size() + 32))) return e;
         HufSlot *hs = d_huf.as<HufSlot>();
         FseSlot *fs = d_fse.as<FseSlot>();
         const FseSlot *pd = c->d_predef;
@@ -312,6 +314,11 @@ struct Submission {
         if (!states.empty()) CU(c, cudaMemcpyAsync(d_states.p, states.data(), states.size() * sizeof(FrameState), cudaMemcpyHostToDevice, stream));
         if (!cta_frames.empty())
             CU(c, cudaMemcpyAsync(d_sched.as<uint8_t>() + 16 + 4 * frames.size(), cta_frames.data(), 4 * cta_frames.size(), cudaMemcpyHostToDevice, stream));
+        if (!frames.empty()) {
+            sched_image.assign(4 + frames.size(), 0u);
+            for (uint32_t f : cta_frames) sched_image[4 + f] = RESUME_SKIP;   // not for the first k_exec launch; k_exec_cta rewrites it
+            CU(c, cudaMemcpyAsync(d_sched.as<uint8_t>() + 16 + 4 * (frames.size() + cta_frames.size()), sched_image.data(), 4 * sched_image.size(), cudaMemcpyHostToDevice, stream));
+        }
         return 0;
     }
     PipelineArgs args(const uint8_t *d_input, uint8_t *d_output, uint64_t out_cap) const {
@@ -322,6 +329,7 @@ struct Submission {
         uint8_t *sp = d_sched.as<uint8_t>();
         a.ticket = (uint32_t *)sp; a.resume = (uint32_t *)(sp + 16); a.cta_frames = (const uint32_t *)(sp + 16 + 4 * frames.size());
         a.n_cta_frames = (uint32_t)cta_frames.size(); a.sched_bytes = (uint32_t)(16 + 4 * frames.size());
+        a.sched_init = (const uint32_t *)(sp + 16 + 4 * (frames.size() + cta_frames.size()));
         return a;
     }
 };
@@ -522,7 +530,7 @@ extern "C" int b200z_batch_run_profile(b200z_batch *b, uint8_t *d_output, size_t
     PipelineArgs a = s.args(b->d_input, d_output, output_cap);
     cudaEvent_t ev[kNumStages + 1];
     for (auto &e : ev) CU(c, cudaEventCreate(&e));
-    if (a.nframes) CU(c, cudaMemsetAsync(a.ticket, 0, a.sched_bytes, c->stream));
+    if (int e = reset_sched(a, c->stream)) return c->set_cuda_err((cudaError_t)e, "reset_sched");
     CU(c, cudaEventRecord(ev[0], c->stream));
     for (int st = 0; st < kNumStages; st++) {
         int e = launch_stage(a, st, c->stream);
@@ -536,9 +544,9 @@ extern "C" int b200z_batch_run_profile(b200z_batch *b, uint8_t *d_output, size_t
     b->ran = true;
     return 0;
 }
-// One pass as b200z_batch_run launches it (k_huf on the side stream beside k_fse), with events on the main stream:
-// out_ms[0..3] = completion time, relative to the start of the pass, of k_setup, of the entropy pair (k_huf || k_fse),
-// of k_exec_cta and of k_exec.
+// One pass as b200z_batch_run launches it, with events on the stream: out_ms[0..3] = completion time, relative to the start of
+// the pass, of k_setup, of k_huf, of the pair k_fse + k_exec (k_exec runs beside k_fse as its programmatic dependent: an event
+// between the two would serialise them) and of k_exec_cta + the k_exec launch that takes what it handed back.
 extern "C" int b200z_batch_run_timeline(b200z_batch *b, uint8_t *d_output, size_t output_cap, float *out_ms, size_t n) {
     if (!b || !out_ms || n < 4) return B200Z_ERR_INVALID_ARGUMENT;
     b200z_ctx *c = b->ctx;
@@ -547,25 +555,18 @@ extern "C" int b200z_batch_run_timeline(b200z_batch *b, uint8_t *d_output, size_
     if (!s.states.empty())
         CU(c, cudaMemcpyAsync(s.d_states.p, b->d_states_init.p, s.states.size() * sizeof(FrameState), cudaMemcpyDeviceToDevice, c->stream));
     PipelineArgs a = s.args(b->d_input, d_output, output_cap);
-    if (a.nframes) CU(c, cudaMemsetAsync(a.ticket, 0, a.sched_bytes, c->stream));
+    if (int e = reset_sched(a, c->stream)) return c->set_cuda_err((cudaError_t)e, "reset_sched");
     cudaEvent_t ev[5];
     for (auto &e : ev) CU(c, cudaEventCreate(&e));
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaEventRecord(ev[0], c->stream));
     int le = launch_stage(a, 0, c->stream);
     CU(c, cudaEventRecord(ev[1], c->stream));
-    if (!le && a.nblocks) {
-        CU(c, cudaEventRecord(c->ev_fork, c->stream));
-        CU(c, cudaStreamWaitEvent(c->side, c->ev_fork, 0));
-        le = launch_stage(a, 2, c->stream);
-        if (!le) le = launch_stage(a, 1, c->side);
-        CU(c, cudaEventRecord(c->ev_join, c->side));
-        CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-    }
+    if (!le) le = launch_stage(a, 1, c->stream);
     CU(c, cudaEventRecord(ev[2], c->stream));
-    if (!le) le = launch_stage(a, 3, c->stream);
+    if (!le) le = launch_fse_exec(a, c->stream);
     CU(c, cudaEventRecord(ev[3], c->stream));
-    if (!le) le = launch_stage(a, 4, c->stream);
+    if (!le) le = launch_cta_rest(a, c->stream);
     CU(c, cudaEventRecord(ev[4], c->stream));
     if (le) return c->set_cuda_err((cudaError_t)le, "launch_stage");
     c->launches += pipeline_launch_count(a);

@@ -46,6 +46,7 @@ __host__ __device__ inline uint32_t seq_sym_resolve(uint32_t v, uint32_t h0, uin
 // BlockAux.flags
 constexpr uint32_t AUX_RAW_OFFSETS = 1u;   // `of` holds raw offset_values (exact path of k_fse); hist_after is not valid
 constexpr uint32_t AUX_WIDE = 2u;          // a prefix sum reached 2^31: positions are only meaningful as differences
+constexpr uint32_t RESUME_SKIP = 0xFFFFFFFFu;   // resume[f]: nothing (left) for k_exec in this frame
 
 // huff0 LUT, split so that it costs 3 KiB of shared memory per block instead of 4 (occupancy: every block of a
 // 1 GiB submission is in flight at once): sym[i] = symbol, nb4[i >> 1] holds the 4-bit code length of entries
@@ -123,7 +124,9 @@ struct alignas(16) BlockAux {
     uint32_t pad;            // sequence-stage status (code | stage << 16); literals-stage status is `status`
     uint32_t hist_after[3];  // offset history after the block (symbolic, seq_sym_*), unless AUX_RAW_OFFSETS
     uint32_t flags;          // AUX_*
-    uint32_t pad2[2];
+    uint32_t ready;          // 1 once the block's sequence stage is over (k_fse): k_exec, launched as k_fse's programmatic
+                             // dependent, starts a frame's block as soon as this is set (block-granular hand-off)
+    uint32_t pad2;
 };
 
 // Per-frame state: carried between submissions for the streaming mirror, fresh for batch frames.

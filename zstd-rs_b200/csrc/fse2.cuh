@@ -33,6 +33,7 @@ __device__ __forceinline__ void f2_st_release(uint32_t a, uint32_t v) { asm vola
 
 __global__ void __launch_bounds__(64) k_fse2(const BlockDesc *__restrict__ descs, BlockAux *__restrict__ aux, const uint8_t *__restrict__ input,
                                             uint32_t *__restrict__ seq_scratch, uint32_t nblocks) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // this CTA is resident: k_exec may follow
     extern __shared__ __align__(16) uint8_t smem_f2[];
     uint16_t *tabs = reinterpret_cast<uint16_t *>(smem_f2);
     uint32_t *s_ll_base = reinterpret_cast<uint32_t *>(smem_f2 + F2_OFF_LUT);
@@ -166,12 +167,7 @@ __global__ void __launch_bounds__(64) k_fse2(const BlockDesc *__restrict__ descs
         if (run && !bad) bad = flags != 0 || br.P != 0;
         const uint32_t bad_mask = __ballot_sync(0xffffffffu, bad || aborted);
         if (lane == 0) { sts32(S_bad, bad_mask); if (aborted) sts32(S_abort, 1u); f2_st_release(S_final, 1u); }
-        // verdicts (blocks the fast path gave up on are decoded again by the exact path -- on the value warp, whose own
-        // stores to the block's records come first in its program order)
-        if (active) {
-            if (!run) aux[b].pad = st_seq;
-            else if (aborted) aux[b].pad = mk_status(B200Z_ERR_CUDA, B200Z_STAGE_SEQUENCES);
-        }
+        // (verdicts are written by the value warp, whose own stores to the block's records come first in its program order)
     } else {
         // ============================================================ value warp
         const bool mine = run && !bad;   // (the chain warp may still give the block up: bad_mask at the end)
@@ -243,6 +239,10 @@ __global__ void __launch_bounds__(64) k_fse2(const BlockDesc *__restrict__ descs
         if (run && !aborted && ((bad_mask >> lane) & 1u)) {
             const uint16_t *TL = tabs + lane * FSE_TAB_U16;
             fse_exact_block(d, aux, b, input, seq_scratch, TL, TL + 512, TL + 1024, tl, to, tm, s_ll_base, s_ml_base, s_ll_bits, s_ml_bits, st_seq);
+        } else if (active && !run) {
+            aux[b].pad = st_seq;
+        } else if (run && aborted) {
+            aux[b].pad = mk_status(B200Z_ERR_CUDA, B200Z_STAGE_SEQUENCES);
         } else if (mine && !aborted) {
             aux[b].pad = 0;
             aux[b].hist_after[0] = h0; aux[b].hist_after[1] = h1; aux[b].hist_after[2] = h2;
@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(64) k_fse2(const BlockDesc *__restrict__ descs
             aux[b].flags = (ovf >> 31) ? AUX_WIDE : 0u;
             aux[b].out_size = (ovf >> 31) ? 0xffffffffu : out_end - lit_end + d->regen_size;   // sum of ml + regenerated literals
         }
+        if (active) fse_publish_ready(aux, b);   // hand-off to k_exec
     }
 }
 

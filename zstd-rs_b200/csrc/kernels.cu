@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(const BlockDesc *__r
         BlockAux a;
         a.status = st_lit;   // literals-stage status; the sequence-stage status travels in `pad` until k_exec orders them
         a.out_size = 0; a.lit_streams_off = lit_streams_off; a.seq_bits_off = seq_bits_off; a.sum_ll = 0; a.pad = st_seq;
-        a.hist_after[0] = a.hist_after[1] = a.hist_after[2] = 0; a.flags = 0; a.pad2[0] = a.pad2[1] = 0;
+        a.hist_after[0] = a.hist_after[1] = a.hist_after[2] = 0; a.flags = 0; a.ready = 0; a.pad2 = 0;
         aux[b] = a;
     }
 }
@@ -492,6 +492,12 @@ __device__ __forceinline__ uint32_t offset_history_step(uint32_t of, uint32_t ll
     return actual;
 }
 
+// hand-off to k_exec (which may run concurrently): results first, fence, then the flag
+__device__ __forceinline__ void fse_publish_ready(BlockAux *aux, uint32_t b) {
+    __threadfence();
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(&aux[b].ready), "r"(1u) : "memory");
+}
+
 struct FseState {
     uint32_t e;   // current 16-bit entry
     __device__ __forceinline__ uint32_t sym() const { return e >> 10; }
@@ -655,6 +661,7 @@ __device__ __noinline__ void fse_exact_block(const BlockDesc *d, BlockAux *aux, 
 
 __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs, BlockAux *__restrict__ aux, const uint8_t *__restrict__ input,
                                           uint32_t *__restrict__ seq_scratch, uint32_t nblocks) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // this CTA is resident: k_exec may follow (launch_pipeline_overlapped)
     extern __shared__ __align__(16) uint8_t smem_fse[];
     uint16_t *tabs = reinterpret_cast<uint16_t *>(smem_fse);
     uint32_t *s_ll_base = reinterpret_cast<uint32_t *>(smem_fse + FSE_BLOCKS_PER_CTA * FSE_TAB_U16 * 2);
@@ -811,6 +818,10 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
         const uint16_t *TL = tabs + (FSE_CHAINS * lane + k) * FSE_TAB_U16;
         fse_exact_block(c.d, aux, c.b, input, seq_scratch, TL, TL + 512, TL + 1024, c.tl, c.to, c.tm, s_ll_base, s_ml_base, s_ll_bits, s_ml_bits, c.st_seq);
     }
+    // hand-off: the block's records, verdict and sizes are in memory
+#pragma unroll
+    for (int k = 0; k < (int)FSE_CHAINS; k++)
+        if (ch[k].active) fse_publish_ready(aux, ch[k].b);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -921,6 +932,28 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) {
     asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Block-granular hand-off from k_fse (fse_publish_ready): k_exec may be launched as k_fse's programmatic dependent and then
+// runs beside it; a frame's block is executed as soon as its sequence stage is over.  Bounded by wall clock (globaltimer),
+// generously: the producer always shows up (all of k_fse's CTAs are resident before k_exec's first one, programmatic
+// dependent launch), a timeout means the device is shared or being debugged -- it is reported as B200Z_ERR_CUDA for the
+// frame instead of hanging the GPU.  Warp-uniform result.
+__device__ __forceinline__ bool exec_wait_ready(const BlockAux *aux, uint32_t b, uint32_t lane) {
+    uint32_t ok = 1;
+    if (lane == 0) {
+        if (ld_acquire_u32(&aux[b].ready) == 0u) {
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            for (;;) {
+                __nanosleep(500);
+                if (ld_acquire_u32(&aux[b].ready) != 0u) break;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 20000000000ull) { ok = 0; break; }   // 20 s
+            }
+        }
+    }
+    return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
+
 #ifndef B200Z_EXEC_WARPS
 #define B200Z_EXEC_WARPS 4
 #endif
@@ -945,7 +978,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                                                         const FrameDesc *__restrict__ frames, FrameState *__restrict__ states,
                                                         const uint8_t *__restrict__ input, const uint8_t *__restrict__ lit_scratch,
                                                         const uint32_t *__restrict__ seq_scratch, uint8_t *__restrict__ output, uint64_t output_cap,
-                                                        uint32_t nframes, const uint32_t *__restrict__ resume, uint32_t frame_base) {
+                                                        uint32_t nframes, uint32_t *__restrict__ resume, uint32_t frame_base) {
     __shared__ uint32_t s_mask[EXEC_WARPS][EXEC_MASK_WORDS];
     __shared__ __align__(16) uint2 s_recs[EXEC_WARPS][EXEC_BATCH];
     const uint32_t f = frame_base + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -957,7 +990,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
     const FrameDesc &fd = frames[f];
     // frames (or leading blocks of frames) that k_exec_cta already executed: resume[f] = first block left for this kernel
     const uint32_t first_bi = resume ? resume[f] : 0u;
-    if (first_bi > fd.nblocks) return;   // k_exec_cta finished the frame, final state included
+    if (first_bi > fd.nblocks) return;   // nothing (left) for this launch: RESUME_SKIP, or k_exec_cta finished the frame
     FrameState fs = states[f];
     ExecState st;
     st.h0 = fs.hist[0]; st.h1 = fs.hist[1]; st.h2 = fs.hist[2];
@@ -974,11 +1007,14 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
         // sequence tables + decode, then execution
         uint32_t hs = d.host_status, hpos = hs >> 24;
         hs &= 0x00ffffffu;
+        // the block's sequence stage must be over (k_fse may still be running); its results are then read past the L1
+        if (!exec_wait_ready(aux, b, lane)) { status = mk_status(B200Z_ERR_CUDA, B200Z_STAGE_SEQUENCES); err_block = d.block_in_frame; break; }
+        const uint32_t ax_status = ld_cg_u32(&aux[b].status), ax_pad = ld_cg_u32(&aux[b].pad), ax_flags = ld_cg_u32(&aux[b].flags);
         uint32_t bs = 0;
         if (hs && hpos == 1) bs = hs;
-        else if (aux[b].status) bs = aux[b].status;
+        else if (ax_status) bs = ax_status;
         else if (hs) bs = hs;
-        else if (d.btype == BT_COMPRESSED && d.nseq && aux[b].pad) bs = aux[b].pad;
+        else if (d.btype == BT_COMPRESSED && d.nseq && ax_pad) bs = ax_pad;
         // a block whose sequence stage failed executes nothing: in the reference decode_sequences completes before
         // execute_sequences starts (block_decoder.rs:176-183)
         if (bs) { status = bs; err_block = d.block_in_frame; break; }
@@ -1001,7 +1037,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
             uint32_t e = 0;
             // block-level descriptor fields used inside the batch loop are consumed here once: a first use inside the loop
             // would wait on a scoreboard shared with the record prefetch issued just before it (a full memory latency per batch)
-            uint32_t resolved_u = (aux[b].flags & AUX_RAW_OFFSETS) ? 0u : 1u, nseq_u = d.nseq;
+            uint32_t resolved_u = (ax_flags & AUX_RAW_OFFSETS) ? 0u : 1u, nseq_u = d.nseq;
             const uint32_t *seqs = seq_scratch + d.seq_buf_off * 3;
             asm volatile("" : "+r"(resolved_u), "+r"(nseq_u), "+l"(seqs));
             const bool resolved = resolved_u != 0;
@@ -1204,7 +1240,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
             }
             if (e) { status = mk_status(e, e == B200Z_ERR_TARGET_TOO_SMALL ? B200Z_STAGE_DRAIN : B200Z_STAGE_EXECUTE); err_block = d.block_in_frame; break; }
             if (resolved && d.nseq) {   // the history after the block, in terms of the history at its start
-                const uint32_t a0 = aux[b].hist_after[0], a1 = aux[b].hist_after[1], a2 = aux[b].hist_after[2];
+                const uint32_t a0 = ld_cg_u32(&aux[b].hist_after[0]), a1 = ld_cg_u32(&aux[b].hist_after[1]), a2 = ld_cg_u32(&aux[b].hist_after[2]);
                 st.h0 = seq_sym_resolve(a0, bh0, bh1, bh2); st.h1 = seq_sym_resolve(a1, bh0, bh1, bh2); st.h2 = seq_sym_resolve(a2, bh0, bh1, bh2);
             }
         }
@@ -1216,6 +1252,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
         FrameState &o = states[f];
         o.hist[0] = st.h0; o.hist[1] = st.h1; o.hist[2] = st.h2;
         o.status = status; o.produced = st.produced; o.counter = st.counter; o.error_block = err_block; o.blocks_done = blocks_done;
+        if (resume) resume[f] = RESUME_SKIP;   // a later launch of this kernel in the same pass has nothing to do here
     }
 }
 
@@ -1354,8 +1391,10 @@ int launch_stage(const PipelineArgs &a, int stage, cudaStream_t s) {
             break;
         case 2:
             if (a.nblocks) {
-                // B200Z_FSE=1: round 1's single-warp kernel (kept for A/B measurements); default: chain warp + value warp
-                static const bool one_warp = [] { const char *e = getenv("B200Z_FSE"); return e && e[0] == '1'; }();
+                // default: one warp walks chain and values (106 instructions per sequence).  B200Z_FSE=2: chain warp + value warp
+                // through a shared-memory queue (k_fse2) -- measured slower on B200 (1.34 vs 1.13 ms on C2b: the chain only drops to
+                // 92 instructions and pays for the queue hand-off), kept for A/B runs.
+                static const bool one_warp = [] { const char *e = getenv("B200Z_FSE"); return !(e && e[0] == '2'); }();
                 if (one_warp) k_fse<<<cdiv(a.nblocks, FSE_BLOCKS_PER_CTA), 32, kFseSmem, s>>>(a.descs, a.aux, a.input, a.seq_scratch, a.nblocks);
                 else k_fse2<<<cdiv(a.nblocks, F2_LANES), 64, kFse2Smem, s>>>(a.descs, a.aux, a.input, a.seq_scratch, a.nblocks);
             }
@@ -1390,10 +1429,10 @@ int launch_checksum(const PipelineArgs &a, cudaStream_t s) {
     return (int)cudaGetLastError();
 }
 
-// resume[] and the ticket counter start at zero for every pass
-static int reset_sched(const PipelineArgs &a, cudaStream_t s) {
+// resume[] and the ticket counter start from their initial image for every pass
+int reset_sched(const PipelineArgs &a, cudaStream_t s) {
     if (!a.nframes || !a.ticket) return 0;
-    return (int)cudaMemsetAsync(a.ticket, 0, a.sched_bytes, s);
+    return (int)cudaMemcpyAsync(a.ticket, a.sched_init, a.sched_bytes, cudaMemcpyDeviceToDevice, s);
 }
 
 int launch_pipeline(const PipelineArgs &a, cudaStream_t s) {
@@ -1402,28 +1441,50 @@ int launch_pipeline(const PipelineArgs &a, cudaStream_t s) {
     return 0;
 }
 
-// The two entropy stages are independent of each other (both only need k_setup's tables) and both are latency-bound chains
-// that leave most of the machine idle: k_huf runs on the side stream beside k_fse.  Execution follows when both are done.
+static int launch_exec_warp(const PipelineArgs &a, cudaStream_t s, bool dependent_of_fse) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cdiv(a.nframes, EXEC_WARPS)); cfg.blockDim = dim3(EXEC_WARPS * 32); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = dependent_of_fse ? 1 : 0;
+    return (int)cudaLaunchKernelEx(&cfg, k_exec, a.descs, (const BlockAux *)a.aux, a.frames, a.states, a.input, (const uint8_t *)a.lit_scratch,
+                                   (const uint32_t *)a.seq_scratch, a.output, a.output_cap, a.nframes, a.resume, 0u);
+}
+
+// The shipped launch order.  k_exec (one warp per frame) runs BESIDE k_fse: it is launched in the same stream as k_fse's
+// programmatic dependent (every k_fse CTA executes griddepcontrol.launch_dependents first thing, so all of them are resident
+// before the first k_exec CTA takes an SM; k_exec never calls griddepcontrol.wait) and starts a frame's block as soon as that
+// block's sequence stage is over (BlockAux::ready).  k_fse is a latency-bound chain that leaves most issue slots idle; k_exec is
+// issue-bound.  Frames of k_exec_cta follow when k_fse is complete, then k_exec once more for whatever k_exec_cta handed back.
+// (k_huf beside k_fse on a second stream was measured: no gain -- both want the shared memory of every SM.)
 int launch_pipeline_overlapped(const PipelineArgs &a, const PipelineStreams &ps) {
     int e;
     if ((e = reset_sched(a, ps.main))) return e;
     if ((e = launch_stage(a, 0, ps.main))) return e;
-    const bool fork = a.nblocks && ps.side && ps.fork && ps.join;
-    if (fork) {
-        if ((e = (int)cudaEventRecord(ps.fork, ps.main))) return e;
-        if ((e = (int)cudaStreamWaitEvent(ps.side, ps.fork, 0))) return e;
-        if ((e = launch_stage(a, 2, ps.main))) return e;   // k_fse first: every one of its CTAs must be resident (one wave)
-        if ((e = launch_stage(a, 1, ps.side))) return e;
-        if ((e = (int)cudaEventRecord(ps.join, ps.side))) return e;
-        if ((e = (int)cudaStreamWaitEvent(ps.main, ps.join, 0))) return e;
-    } else {
-        if ((e = launch_stage(a, 1, ps.main))) return e;
-        if ((e = launch_stage(a, 2, ps.main))) return e;
-    }
-    if ((e = launch_stage(a, 3, ps.main))) return e;
-    return launch_stage(a, 4, ps.main);
+    if ((e = launch_stage(a, 1, ps.main))) return e;
+    if ((e = launch_fse_exec(a, ps.main))) return e;
+    return launch_cta_rest(a, ps.main);
 }
 
-uint32_t pipeline_launch_count(const PipelineArgs &a) { return (a.nblocks ? 3u : 0u) + (a.nframes ? 1u : 0u) + (a.nframes && a.n_cta_frames ? 1u : 0u); }
+// k_fse and, beside it, k_exec for the frames of the warp kernel
+int launch_fse_exec(const PipelineArgs &a, cudaStream_t s) {
+    int e;
+    if ((e = launch_stage(a, 2, s))) return e;
+    if (!a.nframes || a.n_cta_frames >= a.nframes) return 0;
+    return launch_exec_warp(a, s, a.nblocks != 0);
+}
+
+// k_exec_cta for its frames, then k_exec for what it handed back
+int launch_cta_rest(const PipelineArgs &a, cudaStream_t s) {
+    if (!a.nframes || !a.n_cta_frames) return 0;
+    if (int e = launch_stage(a, 3, s)) return e;
+    return launch_exec_warp(a, s, false);
+}
+
+// launches of launch_pipeline_overlapped
+uint32_t pipeline_launch_count(const PipelineArgs &a) {
+    return (a.nblocks ? 3u : 0u) + (a.nframes && a.n_cta_frames < a.nframes ? 1u : 0u) + (a.nframes && a.n_cta_frames ? 2u : 0u);
+}
 
 }  // namespace b200z

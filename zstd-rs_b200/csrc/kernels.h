@@ -20,11 +20,13 @@ struct PipelineArgs {
     uint32_t nblocks;
     uint32_t nframes;
     // execution scheduling (one device buffer: ticket counter, resume[nframes], then the frame list of k_exec_cta)
-    uint32_t *ticket;             // 16 bytes; zeroed with resume[] before every pass (sched_bytes)
-    uint32_t *resume;             // [nframes] first block k_exec still has to execute (written by k_exec_cta)
+    uint32_t *ticket;             // 16 bytes (ticket + debug counters), followed by resume[]
+    uint32_t *resume;             // [nframes] first block the next k_exec launch has to execute, RESUME_SKIP = none.  Starts at 0 for
+                                  // the frames of the warp kernel and at RESUME_SKIP for k_exec_cta's frames (which k_exec_cta rewrites)
     const uint32_t *cta_frames;   // [n_cta_frames] frames executed by k_exec_cta
     uint32_t n_cta_frames;
     uint32_t sched_bytes;         // 16 + 4 * nframes
+    const uint32_t *sched_init;   // device image of the first sched_bytes, copied over ticket/resume before every pass
 };
 
 int init_kernels();  // per-device function attributes (dynamic shared memory); call once per context
@@ -32,10 +34,13 @@ int launch_predefined(FseSlot *predef, cudaStream_t s);
 constexpr int kNumStages = 5;
 extern const char *const kStageNames[kNumStages];
 int launch_stage(const PipelineArgs &a, int stage, cudaStream_t s);
-int launch_pipeline(const PipelineArgs &a, cudaStream_t s);
+int reset_sched(const PipelineArgs &a, cudaStream_t s);      // ticket / resume[] back to their initial image (start of every pass)
+int launch_pipeline(const PipelineArgs &a, cudaStream_t s);   // the stages one after the other (profiling, streaming decoder)
 int launch_checksum(const PipelineArgs &a, cudaStream_t s);   // optional 5th stage: XXH64 of every frame's plaintext
 struct PipelineStreams { cudaStream_t main, side; cudaEvent_t fork, join; };
-int launch_pipeline_overlapped(const PipelineArgs &a, const PipelineStreams &ps);   // k_huf on `side` beside k_fse on `main`
+int launch_pipeline_overlapped(const PipelineArgs &a, const PipelineStreams &ps);   // the shipped order: k_exec beside k_fse (programmatic dependent launch)
+int launch_fse_exec(const PipelineArgs &a, cudaStream_t s);    // k_fse + (beside it) k_exec for the warp kernel's frames
+int launch_cta_rest(const PipelineArgs &a, cudaStream_t s);    // k_exec_cta + k_exec for what it handed back
 uint32_t pipeline_launch_count(const PipelineArgs &a);
 
 }  // namespace b200z
