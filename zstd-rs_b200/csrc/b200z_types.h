@@ -126,7 +126,9 @@ struct alignas(16) BlockAux {
     uint32_t flags;          // AUX_*
     uint32_t ready;          // 1 once the block's sequence stage is over (k_fse): k_exec, launched as k_fse's programmatic
                              // dependent, starts a frame's block as soon as this is set (block-granular hand-off)
-    uint32_t pad2;
+    uint32_t progress;       // sequences whose records k_fse's fast path has published so far (monotone; k_exec consumes them as they
+                             // appear).  If the fast path gives the block up afterwards, the exact path rewrites the records with
+                             // raw offsets and sets AUX_RAW_OFFSETS: k_exec then rolls the block back and runs it again.
 };
 
 // Per-frame state: carried between submissions for the streaming mirror, fresh for batch frames.

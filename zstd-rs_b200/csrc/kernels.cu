@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(const BlockDesc *__r
         BlockAux a;
         a.status = st_lit;   // literals-stage status; the sequence-stage status travels in `pad` until k_exec orders them
         a.out_size = 0; a.lit_streams_off = lit_streams_off; a.seq_bits_off = seq_bits_off; a.sum_ll = 0; a.pad = st_seq;
-        a.hist_after[0] = a.hist_after[1] = a.hist_after[2] = 0; a.flags = 0; a.ready = 0; a.pad2 = 0;
+        a.hist_after[0] = a.hist_after[1] = a.hist_after[2] = 0; a.flags = 0; a.ready = 0; a.progress = 0;
         aux[b] = a;
     }
 }
@@ -493,6 +493,10 @@ __device__ __forceinline__ uint32_t offset_history_step(uint32_t of, uint32_t ll
 }
 
 // hand-off to k_exec (which may run concurrently): results first, fence, then the flag
+__device__ __forceinline__ void fse_publish_progress(BlockAux *aux, uint32_t b, uint32_t nseq_done) {
+    __threadfence();
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(&aux[b].progress), "r"(nseq_done) : "memory");
+}
 __device__ __forceinline__ void fse_publish_ready(BlockAux *aux, uint32_t b) {
     __threadfence();
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(&aux[b].ready), "r"(1u) : "memory");
@@ -787,6 +791,7 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
                 for (int q = 0; q < 4; q++) { fse_step(c, qLL, qML, stage[3 * q], stage[3 * q + 1], stage[3 * q + 2], true); if (q & 1) c.br.service(); }
                 fse_group_end(c, stage);
                 if (c.flags) break;
+                if (((c.i + 4) & 127u) == 0) fse_publish_progress(aux, c.b, c.i + 4);   // every 128 sequences: the fence costs ~1 us
             }
         }
         if (!c.flags) {
@@ -1007,14 +1012,18 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
         // sequence tables + decode, then execution
         uint32_t hs = d.host_status, hpos = hs >> 24;
         hs &= 0x00ffffffu;
-        // the block's sequence stage must be over (k_fse may still be running); its results are then read past the L1
-        if (!exec_wait_ready(aux, b, lane)) { status = mk_status(B200Z_ERR_CUDA, B200Z_STAGE_SEQUENCES); err_block = d.block_in_frame; break; }
-        const uint32_t ax_status = ld_cg_u32(&aux[b].status), ax_pad = ld_cg_u32(&aux[b].pad), ax_flags = ld_cg_u32(&aux[b].flags);
+        // k_fse may still be running (this kernel is its programmatic dependent).  The literals stage is complete (stream order);
+        // the sequence stage of this block is over once BlockAux::ready is set -- until then its records are consumed as the
+        // fast path of k_fse publishes them (BlockAux::progress).  Results of k_fse are read past the L1.
+        const bool seq_block = d.btype == BT_COMPRESSED && d.nseq != 0 && !hs;
+        bool known = !seq_block || __shfl_sync(0xffffffffu, lane == 0 ? ld_acquire_u32(&aux[b].ready) : 0u, 0) != 0u;   // the sequence stage's verdict is in
+        const uint32_t ax_status = ld_cg_u32(&aux[b].status);
+        uint32_t ax_pad = seq_block && known ? ld_cg_u32(&aux[b].pad) : 0u, ax_flags = seq_block && known ? ld_cg_u32(&aux[b].flags) : 0u;
         uint32_t bs = 0;
         if (hs && hpos == 1) bs = hs;
         else if (ax_status) bs = ax_status;
         else if (hs) bs = hs;
-        else if (d.btype == BT_COMPRESSED && d.nseq && ax_pad) bs = ax_pad;
+        else if (ax_pad) bs = ax_pad;
         // a block whose sequence stage failed executes nothing: in the reference decode_sequences completes before
         // execute_sequences starts (block_decoder.rs:176-183)
         if (bs) { status = bs; err_block = d.block_in_frame; break; }
@@ -1033,8 +1042,13 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
             if (d.lit_type == LT_RAW) lit.p = input + d.src_off + d.lit_off;
             else if (d.lit_type == LT_RLE) { lit.p = nullptr; lit.rle = 1; lit.byte = input[d.src_off + d.lit_off]; }
             else lit.p = lit_scratch + d.lit_buf_off;
+            const ExecState saved = st;   // the block's start: where a sequence-stage error / a replay by the exact path rolls back to
+            uint32_t redo = 0;            // 1: sequence-stage error after records were consumed, 2: the records were rewritten with raw offsets
+          exec_block_again:
+            st = saved;
             st.litpos = 0;
             uint32_t e = 0;
+            uint32_t avail = known ? 0xFFFFFFFFu : 0u;   // records that may be read
             // block-level descriptor fields used inside the batch loop are consumed here once: a first use inside the loop
             // would wait on a scoreboard shared with the record prefetch issued just before it (a full memory latency per batch)
             uint32_t resolved_u = (ax_flags & AUX_RAW_OFFSETS) ? 0u : 1u, nseq_u = d.nseq;
@@ -1050,6 +1064,31 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
             const uint32_t bh0 = st.h0, bh1 = st.h1, bh2 = st.h2;   // history at the block's start: what the symbols refer to
             for (uint32_t base = 0; base < nseq_u && !e; base += EXEC_BATCH) {
                 const uint32_t nb = nseq_u - base < EXEC_BATCH ? nseq_u - base : EXEC_BATCH;
+                if (avail < base + nb) {   // wait for k_fse: either these records, or the end of the block's sequence stage
+                    uint32_t got = 0, fin = 0;
+                    if (lane == 0) {
+                        unsigned long long t0 = 0, t1;
+                        for (uint32_t spins = 0;; spins++) {
+                            fin = ld_acquire_u32(&aux[b].ready);
+                            if (fin) break;
+                            got = ld_acquire_u32(&aux[b].progress);
+                            if (got >= base + nb) break;
+                            __nanosleep(200);
+                            if ((spins & 1023u) == 0) {
+                                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                                if (t0 == 0) t0 = t1; else if (t1 - t0 > 20000000000ull) { fin = 2; break; }   // 20 s: see exec_wait_ready
+                            }
+                        }
+                    }
+                    fin = __shfl_sync(0xffffffffu, fin, 0); got = __shfl_sync(0xffffffffu, got, 0);
+                    if (fin == 2) { e = B200Z_ERR_CUDA; break; }
+                    if (fin) {
+                        known = true; avail = 0xFFFFFFFFu;
+                        ax_pad = ld_cg_u32(&aux[b].pad); ax_flags = ld_cg_u32(&aux[b].flags);
+                        if (ax_pad) { redo = 1; break; }
+                        if (ax_flags & AUX_RAW_OFFSETS) { redo = 2; break; }   // (the records consumed so far were symbolic: run the block again)
+                    } else avail = got;
+                }
                 uint32_t lls[K], mls[K], ofs[K], pe_out[K], pe_lit[K];
                 bool on[K];
                 const uint32_t old_out = carry_out, old_lit = carry_lit;
@@ -1238,7 +1277,21 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                     st.produced += rest; st.counter += rest;
                 }
             }
-            if (e) { status = mk_status(e, e == B200Z_ERR_TARGET_TOO_SMALL ? B200Z_STAGE_DRAIN : B200Z_STAGE_EXECUTE); err_block = d.block_in_frame; break; }
+            if (!known && !redo && e != B200Z_ERR_CUDA) {
+                // everything was consumed (or an execution error came up) before the sequence stage's verdict: it decides
+                if (!exec_wait_ready(aux, b, lane)) e = B200Z_ERR_CUDA;
+                else {
+                    known = true;
+                    ax_pad = ld_cg_u32(&aux[b].pad); ax_flags = ld_cg_u32(&aux[b].flags);
+                    if (ax_pad) redo = 1; else if (ax_flags & AUX_RAW_OFFSETS) redo = 2;
+                }
+            }
+            if (redo == 2) { redo = 0; goto exec_block_again; }
+            if (redo == 1) {   // decode_sequences failed: the reference executes nothing of this block (block_decoder.rs:176-183)
+                st = saved;
+                status = ax_pad; err_block = d.block_in_frame; break;
+            }
+            if (e) { status = mk_status(e, e == B200Z_ERR_CUDA ? B200Z_STAGE_SEQUENCES : (e == B200Z_ERR_TARGET_TOO_SMALL ? B200Z_STAGE_DRAIN : B200Z_STAGE_EXECUTE)); err_block = d.block_in_frame; break; }
             if (resolved && d.nseq) {   // the history after the block, in terms of the history at its start
                 const uint32_t a0 = ld_cg_u32(&aux[b].hist_after[0]), a1 = ld_cg_u32(&aux[b].hist_after[1]), a2 = ld_cg_u32(&aux[b].hist_after[2]);
                 st.h0 = seq_sym_resolve(a0, bh0, bh1, bh2); st.h1 = seq_sym_resolve(a1, bh0, bh1, bh2); st.h2 = seq_sym_resolve(a2, bh0, bh1, bh2);
