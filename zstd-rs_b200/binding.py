@@ -350,7 +350,7 @@ class Batch:
         op, ol, _k = _ptr(d_output)
         ms = (C.c_float * 4)()
         self.ctx._chk(self.ctx.L.b200z_batch_run_timeline(self.h, op, ol, ms, 4))
-        return {"k_setup": float(ms[0]), "k_huf": float(ms[1]), "k_fse+k_exec": float(ms[2]), "k_exec_cta+k_exec": float(ms[3])}
+        return {"k_setup+k_huf": float(ms[1]), "k_fse+k_exec": float(ms[2]), "k_exec_cta+k_exec": float(ms[3])}
 
     def finish(self):
         res = np.zeros(len(self.frames), dtype=FRAME_RESULT_DTYPE)

@@ -544,8 +544,8 @@ extern "C" int b200z_batch_run_profile(b200z_batch *b, uint8_t *d_output, size_t
     b->ran = true;
     return 0;
 }
-// One pass as b200z_batch_run launches it, with events on the stream: out_ms[0..3] = completion time, relative to the start of
-// the pass, of k_setup, of k_huf, of the pair k_fse + k_exec (k_exec runs beside k_fse as its programmatic dependent: an event
+// One pass as b200z_batch_run launches it, with events on the stream: out_ms[0] = 0, out_ms[1..3] = completion time, relative to
+// the start of the pass, of the table builds + k_huf (two streams), of the pair k_fse + k_exec (k_exec runs beside k_fse as its programmatic dependent: an event
 // between the two would serialise them) and of k_exec_cta + the k_exec launch that takes what it handed back.
 extern "C" int b200z_batch_run_timeline(b200z_batch *b, uint8_t *d_output, size_t output_cap, float *out_ms, size_t n) {
     if (!b || !out_ms || n < 4) return B200Z_ERR_INVALID_ARGUMENT;
@@ -560,9 +560,9 @@ extern "C" int b200z_batch_run_timeline(b200z_batch *b, uint8_t *d_output, size_
     for (auto &e : ev) CU(c, cudaEventCreate(&e));
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaEventRecord(ev[0], c->stream));
-    int le = launch_stage(a, 0, c->stream);
+    PipelineStreams ps{c->stream, c->side, c->ev_fork, c->ev_join};
     CU(c, cudaEventRecord(ev[1], c->stream));
-    if (!le) le = launch_stage(a, 1, c->stream);
+    int le = launch_tables_literals(a, ps);
     CU(c, cudaEventRecord(ev[2], c->stream));
     if (!le) le = launch_fse_exec(a, c->stream);
     CU(c, cudaEventRecord(ev[3], c->stream));

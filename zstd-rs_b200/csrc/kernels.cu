@@ -60,7 +60,9 @@ __device__ int setup_seq_table_warp(SetupScratch &sc, uint32_t mode, const uint8
 }
 
 __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(const BlockDesc *__restrict__ descs, BlockAux *__restrict__ aux,
-                                                          const uint8_t *__restrict__ input, uint32_t nblocks) {
+                                                          const uint8_t *__restrict__ input, uint32_t nblocks, uint32_t parts) {
+    // parts: bit 0 = the literals side (Huffman table + its BlockAux fields), bit 1 = the sequences side (FSE tables + the rest of
+    // BlockAux).  The two sides are independent: the shipped launch order runs them as two launches on two streams.
     __shared__ SetupScratch scratch[SETUP_WARPS];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t b = blockIdx.x * SETUP_WARPS + warp;
@@ -70,7 +72,8 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(const BlockDesc *__r
     uint32_t st_lit = 0, st_seq = 0, lit_streams_off = 0, seq_bits_off = 0;
     if (d.btype == BT_COMPRESSED && !(d.host_status && (d.host_status >> 24) == 1)) {
         const uint8_t *content = input + d.src_off;
-        if (d.lit_type == LT_COMPRESSED) {
+        if (!(parts & 1u)) {
+        } else if (d.lit_type == LT_COMPRESSED) {
             uint32_t used = 0, nweights = 0;
             int e = 0;
             if (lane == 0) e = huf_read_weights_scratch(content + d.lit_off, d.lit_comp_size, sc.weights, nweights, used, sc.probs, sc.wtab, sc.wcount);
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(const BlockDesc *__r
         } else if (d.lit_type == LT_TREELESS) {
             if (d.huf == nullptr) st_lit = mk_status(B200Z_ERR_LIT_UNINITIALIZED_HUFFMAN_TABLE, B200Z_STAGE_LITERALS);
         }
-        if (d.nseq != 0 && !d.host_status) {
+        if ((parts & 2u) && d.nseq != 0 && !d.host_status) {
             // a table whose build fails (or is never reached) must read as uninitialised to every later user of the slot
             if (lane == 0 && d.fse_build) { d.fse_build->ll.valid = 0; d.fse_build->ll.log = 0; d.fse_build->of.valid = 0; d.fse_build->of.log = 0; d.fse_build->ml.valid = 0; d.fse_build->ml.log = 0; }
             __syncwarp();
@@ -99,11 +102,12 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(const BlockDesc *__r
         }
     }
     if (lane == 0) {
-        BlockAux a;
-        a.status = st_lit;   // literals-stage status; the sequence-stage status travels in `pad` until k_exec orders them
-        a.out_size = 0; a.lit_streams_off = lit_streams_off; a.seq_bits_off = seq_bits_off; a.sum_ll = 0; a.pad = st_seq;
-        a.hist_after[0] = a.hist_after[1] = a.hist_after[2] = 0; a.flags = 0; a.ready = 0; a.progress = 0;
-        aux[b] = a;
+        BlockAux &a = aux[b];
+        if (parts & 1u) { a.status = st_lit; a.lit_streams_off = lit_streams_off; }   // literals-stage status; the sequence-stage status travels in `pad` until k_exec orders them
+        if (parts & 2u) {
+            a.out_size = 0; a.seq_bits_off = seq_bits_off; a.sum_ll = 0; a.pad = st_seq;
+            a.hist_after[0] = a.hist_after[1] = a.hist_after[2] = 0; a.flags = 0; a.ready = 0; a.progress = 0;
+        }
     }
 }
 
@@ -986,6 +990,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                                                         uint32_t nframes, uint32_t *__restrict__ resume, uint32_t frame_base) {
     __shared__ uint32_t s_mask[EXEC_WARPS][EXEC_MASK_WORDS];
     __shared__ __align__(16) uint2 s_recs[EXEC_WARPS][EXEC_BATCH];
+    __shared__ ExecState s_saved[EXEC_WARPS];   // the state at the current block's start (kept out of the registers: read only on a rollback)
     const uint32_t f = frame_base + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const uint32_t lane = threadIdx.x & 31, lt = lanemask_lt();
     if (f >= nframes) return;
@@ -1042,10 +1047,12 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
             if (d.lit_type == LT_RAW) lit.p = input + d.src_off + d.lit_off;
             else if (d.lit_type == LT_RLE) { lit.p = nullptr; lit.rle = 1; lit.byte = input[d.src_off + d.lit_off]; }
             else lit.p = lit_scratch + d.lit_buf_off;
-            const ExecState saved = st;   // the block's start: where a sequence-stage error / a replay by the exact path rolls back to
+            // the block's start: where a sequence-stage error / a replay by the exact path rolls back to
+            if (lane == 0) s_saved[threadIdx.x >> 5] = st;
+            __syncwarp();
             uint32_t redo = 0;            // 1: sequence-stage error after records were consumed, 2: the records were rewritten with raw offsets
           exec_block_again:
-            st = saved;
+            st = s_saved[threadIdx.x >> 5];
             st.litpos = 0;
             uint32_t e = 0;
             uint32_t avail = known ? 0xFFFFFFFFu : 0u;   // records that may be read
@@ -1288,7 +1295,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
             }
             if (redo == 2) { redo = 0; goto exec_block_again; }
             if (redo == 1) {   // decode_sequences failed: the reference executes nothing of this block (block_decoder.rs:176-183)
-                st = saved;
+                st = s_saved[threadIdx.x >> 5];
                 status = ax_pad; err_block = d.block_in_frame; break;
             }
             if (e) { status = mk_status(e, e == B200Z_ERR_CUDA ? B200Z_STAGE_SEQUENCES : (e == B200Z_ERR_TARGET_TOO_SMALL ? B200Z_STAGE_DRAIN : B200Z_STAGE_EXECUTE)); err_block = d.block_in_frame; break; }
@@ -1437,7 +1444,7 @@ const char *const kStageNames[kNumStages] = {"k_setup", "k_huf", "k_fse", "k_exe
 // one stage of the pipeline; a stage with nothing to do launches nothing and returns 0
 int launch_stage(const PipelineArgs &a, int stage, cudaStream_t s) {
     switch (stage) {
-        case 0: if (a.nblocks) k_setup<<<cdiv(a.nblocks, SETUP_WARPS), SETUP_WARPS * 32, 0, s>>>(a.descs, a.aux, a.input, a.nblocks); break;
+        case 0: if (a.nblocks) k_setup<<<cdiv(a.nblocks, SETUP_WARPS), SETUP_WARPS * 32, 0, s>>>(a.descs, a.aux, a.input, a.nblocks, 3u); break;
         case 1:
             if (a.nblocks)
                 k_huf<<<cdiv(a.nblocks, HUF_BLOCKS_PER_CTA), 32, kHufSmem, s>>>(a.descs, a.aux, a.input, a.lit_scratch, a.nblocks);
@@ -1514,10 +1521,31 @@ static int launch_exec_warp(const PipelineArgs &a, cudaStream_t s, bool dependen
 int launch_pipeline_overlapped(const PipelineArgs &a, const PipelineStreams &ps) {
     int e;
     if ((e = reset_sched(a, ps.main))) return e;
-    if ((e = launch_stage(a, 0, ps.main))) return e;
-    if ((e = launch_stage(a, 1, ps.main))) return e;
+    if ((e = launch_tables_literals(a, ps))) return e;
     if ((e = launch_fse_exec(a, ps.main))) return e;
     return launch_cta_rest(a, ps.main);
+}
+
+// k_setup (both sides) and k_huf
+int launch_tables_literals(const PipelineArgs &a, const PipelineStreams &ps) {
+    int e;
+    if (a.nblocks && ps.side && ps.fork && ps.join) {
+        // literals side (Huffman tables, then k_huf) on the side stream, beside the FSE table builds on the main stream; both are
+        // done before k_fse starts, so that k_exec stays k_fse's immediate successor
+        if ((e = (int)cudaEventRecord(ps.fork, ps.main))) return e;
+        if ((e = (int)cudaStreamWaitEvent(ps.side, ps.fork, 0))) return e;
+        k_setup<<<cdiv(a.nblocks, SETUP_WARPS), SETUP_WARPS * 32, 0, ps.side>>>(a.descs, a.aux, a.input, a.nblocks, 1u);
+        if ((e = (int)cudaGetLastError())) return e;
+        if ((e = launch_stage(a, 1, ps.side))) return e;
+        if ((e = (int)cudaEventRecord(ps.join, ps.side))) return e;
+        k_setup<<<cdiv(a.nblocks, SETUP_WARPS), SETUP_WARPS * 32, 0, ps.main>>>(a.descs, a.aux, a.input, a.nblocks, 2u);
+        if ((e = (int)cudaGetLastError())) return e;
+        if ((e = (int)cudaStreamWaitEvent(ps.main, ps.join, 0))) return e;
+    } else {
+        if ((e = launch_stage(a, 0, ps.main))) return e;
+        if ((e = launch_stage(a, 1, ps.main))) return e;
+    }
+    return 0;
 }
 
 // k_fse and, beside it, k_exec for the frames of the warp kernel
@@ -1537,7 +1565,7 @@ int launch_cta_rest(const PipelineArgs &a, cudaStream_t s) {
 
 // launches of launch_pipeline_overlapped
 uint32_t pipeline_launch_count(const PipelineArgs &a) {
-    return (a.nblocks ? 3u : 0u) + (a.nframes && a.n_cta_frames < a.nframes ? 1u : 0u) + (a.nframes && a.n_cta_frames ? 2u : 0u);
+    return (a.nblocks ? 4u : 0u) + (a.nframes && a.n_cta_frames < a.nframes ? 1u : 0u) + (a.nframes && a.n_cta_frames ? 2u : 0u);
 }
 
 }  // namespace b200z

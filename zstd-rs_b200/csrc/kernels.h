@@ -39,6 +39,7 @@ int launch_pipeline(const PipelineArgs &a, cudaStream_t s);   // the stages one 
 int launch_checksum(const PipelineArgs &a, cudaStream_t s);   // optional 5th stage: XXH64 of every frame's plaintext
 struct PipelineStreams { cudaStream_t main, side; cudaEvent_t fork, join; };
 int launch_pipeline_overlapped(const PipelineArgs &a, const PipelineStreams &ps);   // the shipped order: k_exec beside k_fse (programmatic dependent launch)
+int launch_tables_literals(const PipelineArgs &a, const PipelineStreams &ps);   // k_setup (literals side + k_huf on `side`, sequences side on `main`)
 int launch_fse_exec(const PipelineArgs &a, cudaStream_t s);    // k_fse + (beside it) k_exec for the warp kernel's frames
 int launch_cta_rest(const PipelineArgs &a, cudaStream_t s);    // k_exec_cta + k_exec for what it handed back
 uint32_t pipeline_launch_count(const PipelineArgs &a);
