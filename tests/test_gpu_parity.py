@@ -130,7 +130,7 @@ def test_dict_corpus(pkg, ctx, manifest):
     dec = pkg.FrameDecoder(ctx)
     dec.add_dict(dic)
     names = sorted(manifest["dict"])
-    for name in names[:40]:
+    for name in names:   # all 207 (tests/dict_test.rs:77-262)
         data = read_golden("dict_tests", "files", name)
         r = dec.reset(data)
         dec.decode_blocks(r, pkg.ALL)
@@ -209,19 +209,26 @@ def test_fuzz_artifacts_without_dict_id(pkg, ctx, oracle, manifest, exec_mode):
         single = (data[4] >> 5) & 1
         pos = 5 + (0 if single else 1)
         data = bytes(data[:4]) + bytes([data[4] & ~3]) + bytes(data[5:pos]) + bytes(data[pos + did:])
-        try:
-            exp, _ = oracle.decode_frame(data); exp_err = None
-        except oracle.OracleError as e:
-            exp, exp_err = None, (zo[e.code].replace("ZO_", ""), e.stage)
         io = np.zeros(1, dtype=pkg.binding.FRAME_IO_DTYPE)
         io[0] = (0, len(data), 0, 4 << 20)
         out = np.zeros((4 << 20) + 16, dtype=np.uint8)
-        res = pkg.decode_frames(ctx, np.frombuffer(data, dtype=np.uint8), io, out, max_window_size=1 << 40)
-        if exp_err is None:
-            assert res[0]["status"] == 0 and out[:res[0]["out_size"]].tobytes() == exp, f
-        elif exp_err[0] != "ERR_WINDOW_SIZE_TOO_BIG":
-            got = (bz[int(res[0]["status"])].replace("B200Z_", ""), int(res[0]["stage"]))
-            assert got == exp_err, (f, got, exp_err)
+        # once with the reference's default window limit (WindowSizeTooBig must come out the same), once with the limit lifted on
+        # both sides so that the block path itself sees the hostile bytes
+        for mw in (0, 1 << 40):
+            d = oracle.FrameDecoder()
+            if mw:
+                d.set_max_window_size(mw)
+            try:
+                r = d.reset(data); d.decode_blocks(r, oracle.ALL); exp = d.collect(); exp_err = None
+            except oracle.OracleError as e:
+                exp, exp_err = None, (zo[e.code].replace("ZO_", ""), e.stage)
+            res = pkg.decode_frames(ctx, np.frombuffer(data, dtype=np.uint8), io, out, max_window_size=mw)
+            if exp_err is None:
+                if len(exp) <= 4 << 20:
+                    assert res[0]["status"] == 0 and out[:res[0]["out_size"]].tobytes() == exp, (f, mw)
+            else:
+                got = (bz[int(res[0]["status"])].replace("B200Z_", ""), int(res[0]["stage"]))
+                assert got == exp_err, (f, mw, got, exp_err)
         n += 1
     assert n >= 25
 
@@ -600,3 +607,59 @@ def test_block_level_entry(pkg, ctx, oracle, manifest, exec_mode):
     wrong[victim]["num_sequences"] += 1
     with pytest.raises(pkg.B200ZError):
         pkg.decode_blocks(ctx, wrong, fr, comp, np.zeros_like(out))
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("config", ["c2a", "c3", "c4", "c5"])
+def test_full_size_configs(pkg, ctx, config):
+    """The other BASELINE.json configs at their FULL sizes (C2a: one chained 1 GiB frame of 8192 blocks; C3: 10,000 x 64 KiB;
+    C4: 4096 x 1 MiB Silesia-mix frames; C5: 100,000 small frames + a 110 KiB raw-content dictionary): every frame succeeds,
+    sizes match and the plaintext is the generator's, byte for byte (size-independent check; small instances of the same
+    configs are compared with the oracle in test_synthetic_configs_small)."""
+    import torch
+    import datagen as G
+    fs = {"c2a": lambda: G.config_c2a(total_bytes=1 << 30, nframes=1, cache=False), "c3": lambda: G.config_c3(nframes=10000, cache=False),
+          "c4": lambda: G.config_c4(nframes=4096, cache=False), "c5": lambda: G.config_c5(nframes=100000, cache=False)}[config]()
+    D = pkg.Dictionary.raw_content(ctx, 1, fs.raw_dict.tobytes()) if fs.raw_dict is not None else None
+    b = pkg.Batch(ctx, fs.comp, fs.frames_io(), forced_dict=D)
+    d_out = torch.zeros(fs.D + 64, dtype=torch.uint8, device="cuda")
+    b.run(d_out)
+    res = b.finish()
+    assert (res["status"] == 0).all(), (config, res[res["status"] != 0][:3])
+    assert (res["out_size"] == fs.out_size).all() and (res["bytes_read"] == fs.src_size).all()
+    got = d_out[:fs.D].cpu().numpy()
+    assert np.array_equal(got, fs.plain), config
+    b.close()
+
+
+def test_exact_path_replay_rolls_back(pkg, ctx, oracle, monkeypatch):
+    """k_exec (one warp per frame) consumes a block's sequences while k_fse is still decoding it; when k_fse's fast path gives the
+    block up late (here: thousands of ordinary text sequences, then one sequence with more than 32 extra bits -- a far offset with
+    a long literal run and a long match) its exact path rewrites the records with raw offsets, and k_exec must roll the block back
+    and run it again.  Large-window frames; all frames forced onto the warp kernel."""
+    import datagen as G
+    monkeypatch.setenv("B200Z_EXEC_MODE", "warp")
+    rng = np.random.Generator(np.random.PCG64(77))
+    pieces = []
+    for i in range(24):
+        far = rng.integers(0, 256, 2 << 20, dtype=np.uint8)
+        text = G.gen_text(100000 + 1000 * i, 500 + i)
+        fresh = rng.integers(0, 256, 20000 + 37 * i, dtype=np.uint8)
+        pieces.append(np.concatenate([far, text, fresh, far[5000:5000 + 9000 + 11 * i]]))
+    frames = [G.compress(p_, level=3, window_log=22) for p_ in pieces]
+    io, comp, total = _io(pkg, frames, [len(p_) for p_ in pieces])
+    import torch
+    b = pkg.Batch(ctx, comp, io)
+    d_out = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        b.run(d_out)
+        res = b.finish()
+        assert (res["status"] == 0).all(), res[res["status"] != 0][:3]
+        out = d_out.cpu().numpy()
+        for i, p_ in enumerate(pieces):
+            assert np.array_equal(out[io[i]["out_off"]:io[i]["out_off"] + len(p_)], p_), i
+    # the exact path really was taken for blocks with many sequences (raw-offset flag), otherwise this test does not test what it says
+    nblocks = b.info()["blocks"]
+    raw_big = [k for k in range(nblocks) if (b.debug_block_flags(k) & 1) and len(b.debug_sequences(k)) > 1000]
+    assert len(raw_big) >= 12, "no long block went through k_fse's exact path"
+    b.close()

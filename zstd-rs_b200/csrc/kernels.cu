@@ -473,6 +473,9 @@ constexpr uint32_t FSE_CHAINS = B200Z_FSE_CHAINS;            // blocks per lane,
 constexpr uint32_t FSE_LANES = B200Z_FSE_LANES;              // lanes of the warp that carry blocks
 constexpr uint32_t FSE_BLOCKS_PER_CTA = FSE_LANES * FSE_CHAINS;
 constexpr uint32_t FSE_TAB_U16 = 512 + 512 + 256;   // LL, ML, OF entries per block
+#ifndef B200Z_FSE_PUBLISH
+#define B200Z_FSE_PUBLISH 128u   // sequences between two progress publications (power of two, multiple of 4)
+#endif
 
 __constant__ uint32_t c_ll_base[36] = {0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,18,20,22,24,28,32,40,48,64,128,256,512,1024,2048,4096,8192,16384,32768,65536};
 __constant__ uint8_t c_ll_bits[36] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,6,7,8,9,10,11,12,13,14,15,16};
@@ -795,7 +798,7 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
                 for (int q = 0; q < 4; q++) { fse_step(c, qLL, qML, stage[3 * q], stage[3 * q + 1], stage[3 * q + 2], true); if (q & 1) c.br.service(); }
                 fse_group_end(c, stage);
                 if (c.flags) break;
-                if (((c.i + 4) & 127u) == 0) fse_publish_progress(aux, c.b, c.i + 4);   // every 128 sequences: the fence costs ~1 us
+                if (((c.i + 4) & (B200Z_FSE_PUBLISH - 1u)) == 0) fse_publish_progress(aux, c.b, c.i + 4);   // the fence costs ~1 us
             }
         }
         if (!c.flags) {
