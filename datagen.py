@@ -146,7 +146,9 @@ def gen_text(nbytes, seed, zipf_s=1.05, reuse=0.50, run_lo=3, run_hi=24):
     np.clip(ids, 0, nw - 1, out=ids)
     # phrase re-use: overwrite runs of word ids with a copy of an earlier run (up to ~10k words back ~ 64 KiB)
     nruns = int(n * reuse / ((run_lo + run_hi) / 2))
-    starts = rng.integers(64, n - run_hi - 1, nruns)
+    if n - run_hi - 1 <= 64:   # a segment of a few dozen words: nothing to re-use from
+        nruns = 0
+    starts = rng.integers(64, max(65, n - run_hi - 1), nruns)
     lens = rng.integers(run_lo, run_hi, nruns)
     back = rng.integers(8, 10000, nruns)
     for s, ln, bk in zip(starts.tolist(), lens.tolist(), back.tolist()):
