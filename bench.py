@@ -430,8 +430,6 @@ def main():
         m["D_total"] = fs_all.D * world if mode == "weak" else fs_all.D
         m["C_total"] = fs_all.C * world if mode == "weak" else fs_all.C
         runs[mode] = m
-        if mode != order[-1]:
-            m["batch"].close(); m["d_out"] = None
     main_mode = args.scaling if world > 1 else "weak"
     M = runs[main_mode]
     fs, batch, d_out = M["fs"], M["batch"], M["d_out"]
