@@ -980,7 +980,8 @@ constexpr uint32_t EXEC_TMAX = B200Z_EXEC_TMAX;             // most bytes one ba
 #ifndef B200Z_EXEC_PREFETCH
 #define B200Z_EXEC_PREFETCH 1
 #endif
-constexpr uint32_t EXEC_MASK_WORDS = ((EXEC_TMAX + 3 + 127) / 128) * 4 + 4;   // rows of 128 bytes (4 words) on the 4-byte grid of the output
+constexpr uint32_t EXEC_CHUNK_ROWS = B200Z_EXEC_CHUNK_ROWS;                    // rows (of 32 bytes) whose loads are in flight together
+constexpr uint32_t EXEC_MASK_WORDS = (EXEC_TMAX + 31) / 32 + EXEC_CHUNK_ROWS;
 #ifndef B200Z_EXEC_MINB
 #define B200Z_EXEC_MINB 8
 #endif
@@ -1177,13 +1178,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                 // Sequence j owns the bytes [lit_begin_j, out_end_j): its literal run, then its match.  A bit is set at
                 // the last byte of every sequence, so the owner of output byte q is the number of set bits below q;
                 // one 8-byte shared-memory record per sequence then tells the byte where it comes from.
-                // Rows of 128 bytes, FOUR bytes per lane, laid out on the output's 4-byte grid: p = q + mis, where q is the batch-relative
-                // position and mis = (address of the batch's first byte) & 3, so that a lane's word is an aligned 32-bit store.
-                const uint8_t *litq0 = lit.p + st.litpos;
-                uint8_t *bout0 = out + st.produced;
-                const uint32_t mis = (uint32_t)((uintptr_t)bout0 & 3u);
-                const uint32_t Tp = T + mis;                      // rows cover p in [0, Tp); bytes below mis belong to the previous batch
-                const uint32_t nrows = (Tp + 127u) >> 7;
+                const uint32_t nrows = (T + 31) >> 5;
                 // The batch's match sources are scattered over the frame's window, and with thousands of frames in flight the
                 // windows do not stay in L2: ask for the sectors now, a few hundred instructions before the rows need them.
                 if (B200Z_EXEC_PREFETCH) {
@@ -1200,84 +1195,88 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                         prefetch_l2(lit.p + (ahead < lit.regen ? ahead : lit.regen - 1));
                     }
                 }
-                for (uint32_t w = lane; w < nrows * 4u; w += 32) sts32(a_mask + (w << 2), 0u);
-                // 8-byte record: x = match start | (match bytes of the earlier sequences) << 16, both in p coordinates (<= EXEC_TMAX + 3:
-                // 16 bits each); literal byte p of the sequence is literal number p - x.hi of the batch, match byte p comes from p - offset
+                sts32(a_mask + (lane << 2), 0u);
+                if (nrows > 32u - EXEC_CHUNK_ROWS)
+                    for (uint32_t w = lane + 32; w < ((nrows + EXEC_CHUNK_ROWS - 1u) & ~(EXEC_CHUNK_ROWS - 1u)); w += 32) sts32(a_mask + (w << 2), 0u);
+                // 8-byte record: literal byte q of the sequence is literal number (q - m_before) of the batch (m_before = match bytes
+                // of the earlier sequences = match start - literal end), match byte q comes from output position q - offset
+                // (m_start, m_before <= EXEC_TMAX: 16 bits each)
 #pragma unroll
                 for (uint32_t k = 0; k < K; k += 2)
-                    sts128(a_recs + ((K * lane + k) << 3), (mstart[k] + mis) | ((mstart[k] - lend[k] + mis) << 16), offs[k],
-                           (mstart[k + 1] + mis) | ((mstart[k + 1] - lend[k + 1] + mis) << 16), offs[k + 1]);
+                    sts128(a_recs + ((K * lane + k) << 3), mstart[k] | ((mstart[k] - lend[k]) << 16), offs[k], mstart[k + 1] | ((mstart[k + 1] - lend[k + 1]) << 16), offs[k + 1]);
                 const bool has_ovl = __any_sync(0xffffffffu, ovl);   // some match overlaps its own output (rare)
                 __syncwarp();
 #pragma unroll
                 for (uint32_t k = 0; k < K; k++)
-                    if (on[k]) red_or_shared(a_mask + (((oend[k] - 1 + mis) >> 5) << 2), 1u << ((oend[k] - 1 + mis) & 31u));
+                    if (on[k]) red_or_shared(a_mask + (((oend[k] - 1) >> 5) << 2), 1u << ((oend[k] - 1) & 31u));
                 __syncwarp();
-                uint8_t *boutp = bout0 - mis;          // boutp[p] is output byte p of the batch
-                const uint8_t *litq = litq0;
-                asm volatile("" : "+l"(boutp), "+l"(litq));   // keep both bases as single 64-bit registers (one add per access)
+                uint8_t *bout = out + st.produced;
+                const uint8_t *litq = lit.p + st.litpos;
+                asm volatile("" : "+l"(bout), "+l"(litq));   // keep both bases as single 64-bit registers (one add per access)
                 uint32_t before = 0;   // sequences ended in earlier rows
-                const uint32_t g = lane >> 3, sh = (lane & 7u) << 2;
-                for (uint32_t r = 0; r < nrows; r++) {
-                    // ---- who owns my four bytes: a bit per sequence end; a 4-byte word spans at most two sequences (match length >= 3)
-                    const uint4 W4 = lds128(a_mask + (r << 4));
-                    const uint32_t pc0 = (uint32_t)__popc(W4.x), pc1 = (uint32_t)__popc(W4.y), pc2 = (uint32_t)__popc(W4.z), pc3 = (uint32_t)__popc(W4.w);
-                    const uint32_t Wg = g == 0 ? W4.x : (g == 1 ? W4.y : (g == 2 ? W4.z : W4.w));
-                    const uint32_t owner0 = before + (g > 0 ? pc0 : 0u) + (g > 1 ? pc1 : 0u) + (g > 2 ? pc2 : 0u) + (uint32_t)__popc(Wg & ((1u << sh) - 1u));
-                    before += pc0 + pc1 + pc2 + pc3;
-                    const uint32_t nib = (Wg >> sh) & 7u;
-                    const uint2 rA = lds64(a_recs + ((owner0 & (EXEC_BATCH - 1u)) << 3)), rB = lds64(a_recs + (((owner0 + 1u) & (EXEC_BATCH - 1u)) << 3));
-                    const uint32_t p0 = (r << 7) + (lane << 2);
-                    const int32_t floor_p = (int32_t)(r << 7);
-                    uint32_t word = 0, pend = 0, okb = 0;
-                    int32_t spk[4];
+                // Rows are produced EXEC_CHUNK_ROWS at a time: every byte whose source lies before the chunk (literals, and
+                // matches reaching back past the chunk start) is loaded first -- EXEC_CHUNK_ROWS independent loads per lane in
+                // flight -- then stored; the few bytes whose source lies inside the chunk follow, row by row.  (Issuing the
+                // next chunk's loads before this chunk's stores was measured slower: more bytes turn dependent.)
+                // The per-byte work is branch-free: one select between the literal and the match source.
+                // tag: TAG_NONE = nothing to do, TAG_STORE = value loaded, otherwise the (batch-relative, >= floor) source
+                // position of a match byte that had to wait.
+                constexpr int32_t TAG_NONE = INT32_MIN, TAG_STORE = INT32_MIN + 1;
+                constexpr int R = (int)EXEC_CHUNK_ROWS;
+                auto load_chunk = [&](uint32_t r0, int32_t floor, uint32_t (&val)[R], int32_t (&tag)[R]) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const bool useB = k > 0 && (nib & ((1u << k) - 1u)) != 0u;
-                        const uint32_t rx = useB ? rB.x : rA.x, off = useB ? rB.y : rA.y;
-                        const uint32_t p = p0 + (uint32_t)k, x = rx & 0xffffu;
-                        const bool valid = p >= mis && p < Tp;
-                        const bool is_match = p >= x;
-                        int32_t sp = (int32_t)p - (int32_t)off;                    // source of a match byte, in p coordinates
-                        if (has_ovl) {                                              // overlapping match: byte kk comes from kk mod offset
-                            const uint32_t kk = p - x;
-                            if (is_match && kk >= off) sp = (int32_t)x - (int32_t)off + (int32_t)(kk % off);
+                    for (int i = 0; i < R; i++) {
+                        const uint32_t q = ((r0 + i) << 5) + lane;
+                        const uint32_t word = lds32(a_mask + ((r0 + i) << 2));
+                        const uint32_t owner = before + __popc(word & lt);   // sequences that ended below q
+                        before += __popc(word);
+                        const uint2 rc = lds64(a_recs + ((owner & (EXEC_BATCH - 1u)) << 3));
+                        const uint32_t mst = rc.x & 0xffffu;
+                        const bool is_match = q >= mst;
+                        int32_t sp = (int32_t)q - (int32_t)rc.y;                  // batch-relative source of a match byte
+                        if (has_ovl) {                                            // overlapping match: byte k comes from k mod offset
+                            const uint32_t kk = q - mst;
+                            if (is_match && kk >= rc.y) sp = (int32_t)mst - (int32_t)rc.y + (int32_t)(kk % rc.y);
                         }
-                        const bool dep = is_match && sp >= floor_p;                 // source inside this row: after the row's other bytes
-                        const uint8_t *bp = is_match ? (const uint8_t *)boutp : litq;
-                        const int32_t idx = is_match ? sp : (int32_t)(p - (rx >> 16));
-                        uint32_t v = 0;
-                        if (valid && !dep) v = bp[idx];
-                        word |= v << (8 * k);
-                        spk[k] = sp;
-                        pend |= (valid && dep) ? (1u << k) : 0u;
-                        okb |= valid ? (1u << k) : 0u;
+                        const bool valid = q < T;
+                        const bool dep = is_match && sp >= floor;
+                        const int32_t idx = is_match ? sp : (int32_t)(q - (rc.x >> 16));
+                        const uint8_t *bp = is_match ? (const uint8_t *)bout : litq;
+                        tag[i] = valid ? (dep ? sp : TAG_STORE) : TAG_NONE;
+                        val[i] = 0;
+                        if (valid && !dep) val[i] = bp[idx];
                     }
-                    if (okb == 15u && pend == 0u) *reinterpret_cast<uint32_t *>(boutp + p0) = word;
-                    else {
+                };
+                auto store_chunk = [&](uint32_t r0, int32_t floor, const uint32_t (&val)[R], const int32_t (&tag)[R]) {
 #pragma unroll
-                        for (int k = 0; k < 4; k++) if (((okb & ~pend) >> k) & 1u) boutp[p0 + k] = (uint8_t)(word >> (8 * k));
-                    }
-                    if (__any_sync(0xffffffffu, pend != 0u)) {
-                        // bytes whose source lies in this row: sources precede destinations, so the lowest pending byte is always ready
-                        for (;;) {
-                            __syncwarp();
-                            const uint32_t pm0 = __ballot_sync(0xffffffffu, pend & 1u), pm1 = __ballot_sync(0xffffffffu, pend & 2u),
-                                           pm2 = __ballot_sync(0xffffffffu, pend & 4u), pm3 = __ballot_sync(0xffffffffu, pend & 8u);
-                            if ((pm0 | pm1 | pm2 | pm3) == 0u) break;
+                    for (int i = 0; i < R; i++)
+                        if (tag[i] == TAG_STORE) bout[((r0 + i) << 5) + lane] = (uint8_t)val[i];
+                    // dependent bytes, rows in order (sources in earlier rows are final, inside the row the lowest pending byte is ready)
+                    bool anydep = false;
 #pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                if (pend & (1u << k)) {
-                                    const uint32_t rel = (uint32_t)(spk[k] - floor_p);
-                                    const uint32_t sb = rel & 3u, sl = rel >> 2;
-                                    const uint32_t pm = sb == 0 ? pm0 : (sb == 1 ? pm1 : (sb == 2 ? pm2 : pm3));
-                                    if (!((pm >> sl) & 1u)) { boutp[p0 + k] = boutp[spk[k]]; pend &= ~(1u << k); }
-                                }
+                    for (int i = 0; i < R; i++) anydep |= tag[i] >= floor;
+                    if (__any_sync(0xffffffffu, anydep)) {
+#pragma unroll
+                        for (int i = 0; i < R; i++) {
+                            bool mine = tag[i] >= floor;
+                            uint32_t pending = __ballot_sync(0xffffffffu, mine);
+                            const int32_t row0 = (int32_t)((r0 + i) << 5);
+                            while (pending) {
+                                __syncwarp();
+                                bool ready = mine && (tag[i] < row0 || !((pending >> (tag[i] - row0)) & 1u));
+                                if (ready) { bout[row0 + (int32_t)lane] = bout[tag[i]]; mine = false; }
+                                pending &= ~__ballot_sync(0xffffffffu, ready);
                             }
                         }
                     }
                     __syncwarp();
+                };
+                for (uint32_t r0 = 0; r0 < nrows; r0 += R) {
+                    uint32_t va[R]; int32_t ta[R];
+                    load_chunk(r0, (int32_t)(r0 << 5), va, ta);
+                    store_chunk(r0, (int32_t)(r0 << 5), va, ta);
                 }
+                __syncwarp();
                 st.produced += T; st.counter += T; st.litpos += L;
             }
             if (!e && st.litpos < lit.regen) {
