@@ -551,8 +551,9 @@ __device__ __forceinline__ void fse_step(FseChain &c, uint32_t qLL, uint32_t qML
     c.max_of = max(c.max_of, cO);   // offset codes >= 30 are checked per group (LL/ML codes are capped by table construction, scratch.rs:36-40)
     // extra bits: OF, ML, LL (get_bits_triple, sequence_section_decoder.rs:185)
     const uint32_t xsum = xO + xM + xL;
-    c.max_x = max(c.max_x, xsum);   // > 32 extra bits in one sequence: not for this path, checked per group
-    const uint32_t t1 = shl_c(hi, xO), t2 = shl_c(t1, xM);
+    c.max_x = max(c.max_x, xsum);   // > 38 extra bits in one sequence (the 64-bit window also has to hold the 26 state bits): not for
+                                    // this path, checked per group.  (Far offsets with long lengths -- 1 MiB+ windows -- stay on this path.)
+    const uint32_t t1 = fsl_c(lo, hi, xO), t2 = shl_c(t1, xM);   // the window below the offset bits: ML and LL extra bits (<= 32 together)
     const uint32_t obits = shr_c(hi, 32u - xO), ml_add = shr_c(t1, 32u - xM), ll_add = shr_c(t2, 32u - xL);
     uint32_t offset = obits + (1u << (cO & 31u));
     const uint32_t ll = (vL & 0xFFFFFFu) + ll_add, ml = (vM & 0xFFFFFFu) + ml_add;
@@ -577,7 +578,8 @@ __device__ __forceinline__ void fse_step(FseChain &c, uint32_t qLL, uint32_t qML
     if (update) {   // state updates LL, ML, OF (:198-207); compact entries (b200z_types.h): nb = log - floor(log2 f)
         const uint32_t fL = c.eL & 1023u, fM = c.eM & 1023u, fO = c.eO & 1023u;
         const uint32_t nbL = c.logL - bfind32(fL), nbM = c.logM - bfind32(fM), nbO = c.logO - bfind32(fO);
-        const uint32_t u0 = fsl_c(lo, hi, xsum);                 // the 32 bits below the extra bits
+        // the bits below the extra bits (up to 26 are used): a clamped funnel shift covers xsum <= 32, the rest comes out of lo
+        const uint32_t u0 = shl_c(fsl_c(lo, hi, xsum), xsum - min(xsum, 32u));
         const uint32_t u1 = shl_c(u0, nbL), u2 = shl_c(u1, nbM);
         const uint32_t aL = shr_c(u0, 32u - nbL), aM = shr_c(u1, 32u - nbM), aO = shr_c(u2, 32u - nbO);
         c.eL = fse_lds16(c.qTL + (((fL << nbL) + aL) << 1));
@@ -587,7 +589,7 @@ __device__ __forceinline__ void fse_step(FseChain &c, uint32_t qLL, uint32_t qML
     } else c.br.P -= (int32_t)xsum;
 }
 __device__ __forceinline__ void fse_group_end(FseChain &c, const uint32_t (&stage)[12]) {
-    c.flags |= (uint32_t)(c.br.P < 0) | (uint32_t)(c.max_x > 32u) | ((c.max_of + 2u) >> 5);   // bits_remaining only decreases: one check per group is equivalent
+    c.flags |= (uint32_t)(c.br.P < 0) | (uint32_t)(c.max_x > 38u) | ((c.max_of + 2u) >> 5);   // bits_remaining only decreases: one check per group is equivalent
     uint4 *o4 = reinterpret_cast<uint4 *>(c.out + 3 * c.i);
     o4[0] = make_uint4(stage[0], stage[1], stage[2], stage[3]);
     o4[1] = make_uint4(stage[4], stage[5], stage[6], stage[7]);
@@ -806,7 +808,7 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
                 uint32_t ll, ml, of;
                 fse_step(c, qLL, qML, ll, ml, of, c.i + 1 < c.nseq);
                 c.br.service();
-                c.flags |= (uint32_t)(c.br.P < 0) | (uint32_t)(c.max_x > 32u) | ((c.max_of + 2u) >> 5);
+                c.flags |= (uint32_t)(c.br.P < 0) | (uint32_t)(c.max_x > 38u) | ((c.max_of + 2u) >> 5);
                 c.out[3 * c.i] = ll; c.out[3 * c.i + 1] = ml; c.out[3 * c.i + 2] = of;
             }
         }
