@@ -79,6 +79,7 @@ __device__ __forceinline__ void xc_bulk_wait0() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void xc_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void xc_fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 __device__ __forceinline__ uint32_t xc_ld_acquire_shared(uint32_t a) { uint32_t v; asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t xc_ld_cg_u32(const uint32_t *p) { uint32_t v; asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ uint32_t xc_ldg_cg_u8(const uint8_t *p) { uint32_t v; asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
 // 8-byte ring record: lo = match start (window position, 18 bits) | literal delta << 18 (low 14 bits),
@@ -234,12 +235,13 @@ __device__ __forceinline__ XcLoad xc_load(const XcBlk &B, uint32_t k, uint32_t t
     for (uint32_t q = 0; q < XC_PER_THREAD; q++) {
         const uint32_t i = i0 + q;
         L.out[q] = 0; L.lit[q] = 0; L.of[q] = 0;
-        if (i < B.nseq) { const uint32_t *p = B.seqs + (uint64_t)i * 3; L.out[q] = p[0]; L.lit[q] = p[1]; L.of[q] = p[2]; }
+        // (past the read-only data path: a raw-offset block's records were rewritten by this kernel a moment ago)
+        if (i < B.nseq) { const uint32_t *p = B.seqs + (uint64_t)i * 3; L.out[q] = xc_ld_cg_u32(p); L.lit[q] = xc_ld_cg_u32(p + 1); L.of[q] = xc_ld_cg_u32(p + 2); }
         else if (i < B.ntot) { L.out[q] = B.out_size; L.lit[q] = B.regen; }   // trailing literals (sequence_execution.rs:40-44)
     }
     L.p_out = 0; L.p_lit = 0;
     // (no shuffle here: the loads stay in flight while the rows of the previous batch are produced)
-    if (lane == 0 && i0 != 0 && i0 <= B.nseq) { const uint32_t *p = B.seqs + (uint64_t)(i0 - 1) * 3; L.p_out = p[0]; L.p_lit = p[1]; }
+    if (lane == 0 && i0 != 0 && i0 <= B.nseq) { const uint32_t *p = B.seqs + (uint64_t)(i0 - 1) * 3; L.p_out = xc_ld_cg_u32(p); L.p_lit = xc_ld_cg_u32(p + 1); }
     return L;
 }
 
@@ -355,7 +357,41 @@ __global__ void __launch_bounds__(XC_THREADS, 1) k_exec_cta(const BlockDesc *__r
                 continue;
             }
             const uint32_t nseq = d.nseq;
-            if (nseq && (ax.pad || (ax.flags & (AUX_RAW_OFFSETS | AUX_WIDE)))) { bailed = true; why |= ax.pad ? 1u : 4u; break; }
+            if (nseq && (ax.pad || (ax.flags & AUX_WIDE))) { bailed = true; why |= ax.pad ? 1u : 4u; break; }
+            if (nseq && (ax.flags & AUX_RAW_OFFSETS)) {
+                // k_fse's exact path left raw offset_values (a sequence with more extra bits than its fast path takes, an offset
+                // code >= 30, ...).  do_offset_history (sequence_execution.rs:59-118) is a serial walk: warp 0 runs it over the block's
+                // records, 32 at a time, and rewrites them in place as resolved offsets -- after which the block is an ordinary one,
+                // for this kernel and (flag cleared, history stored) for k_exec should a later check hand the frame back.
+                uint32_t *sq = const_cast<uint32_t *>(seq_scratch) + d.seq_buf_off * 3;
+                uint32_t big = (h0 | h1 | h2) >> SEQ_SYM_SHIFT;   // values >= 2^30 cannot be told from symbols afterwards
+                for (uint32_t i = tid; i < nseq; i += XC_THREADS) big |= sq[3 * i + 2] >> SEQ_SYM_SHIFT;
+                if (__syncthreads_or((int)big)) { bailed = true; why |= 4u; break; }
+                if (warp == 0) {
+                    uint32_t a0 = h0, a1 = h1, a2 = h2, prev_lit = 0;
+                    for (uint32_t base = 0; base < nseq; base += 32) {
+                        const uint32_t i = base + lane, n = min(32u, nseq - base);
+                        const uint32_t of = i < nseq ? sq[3 * i + 2] : 0u, lit = i < nseq ? sq[3 * i + 1] : 0u;
+                        uint32_t plit = __shfl_up_sync(0xffffffffu, lit, 1);
+                        if (lane == 0) plit = prev_lit;
+                        const uint32_t ll = lit - plit;
+                        uint32_t mine = 0;
+                        for (uint32_t j = 0; j < n; j++) {
+                            const uint32_t actual = offset_history_step(__shfl_sync(0xffffffffu, of, j), __shfl_sync(0xffffffffu, ll, j), a0, a1, a2);
+                            if (lane == j) mine = actual;
+                        }
+                        if (i < nseq) sq[3 * i + 2] = mine;
+                        prev_lit = __shfl_sync(0xffffffffu, lit, n - 1);
+                    }
+                    if (lane == 0) {
+                        BlockAux *axw = const_cast<BlockAux *>(aux) + b;
+                        axw->hist_after[0] = a0; axw->hist_after[1] = a1; axw->hist_after[2] = a2;   // concrete values (< 2^30): resolve to themselves
+                        axw->flags = ax.flags & ~AUX_RAW_OFFSETS;
+                    }
+                }
+                __threadfence();
+                __syncthreads();
+            }
             const uint32_t out_size = ax.out_size, regen = d.regen_size;
             const uint32_t sum_ll = nseq ? ax.sum_ll : 0u;
             if (out_size > XC_WIN_MAX || produced + out_size > cap || sum_ll > regen || regen > out_size) { bailed = true; why |= produced + out_size > cap ? 2u : 8u; break; }
@@ -475,7 +511,7 @@ __global__ void __launch_bounds__(XC_THREADS, 1) k_exec_cta(const BlockDesc *__r
                 else if (tid < 32) { const uint32_t a = tail_beg + (tid - 16u); if (a < B.a_end) B.gout[a - B.woff] = (uint8_t)lds8(S + a); }
             }
             if (nseq) {   // the history after the block, in terms of the history at its start (k_fse, symbolic)
-                const uint32_t a0 = ax.hist_after[0], a1 = ax.hist_after[1], a2 = ax.hist_after[2];
+                const uint32_t a0 = xc_ld_cg_u32(&ax.hist_after[0]), a1 = xc_ld_cg_u32(&ax.hist_after[1]), a2 = xc_ld_cg_u32(&ax.hist_after[2]);
                 const uint32_t n0 = seq_sym_resolve(a0, h0, h1, h2), n1 = seq_sym_resolve(a1, h0, h1, h2), n2 = seq_sym_resolve(a2, h0, h1, h2);
                 h0 = n0; h1 = n1; h2 = n2;
             }

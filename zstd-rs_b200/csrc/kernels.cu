@@ -579,7 +579,8 @@ __device__ __forceinline__ void fse_step(FseChain &c, uint32_t qLL, uint32_t qML
         const uint32_t fL = c.eL & 1023u, fM = c.eM & 1023u, fO = c.eO & 1023u;
         const uint32_t nbL = c.logL - bfind32(fL), nbM = c.logM - bfind32(fM), nbO = c.logO - bfind32(fO);
         // the bits below the extra bits (up to 26 are used): a clamped funnel shift covers xsum <= 32, the rest comes out of lo
-        const uint32_t u0 = shl_c(fsl_c(lo, hi, xsum), xsum - min(xsum, 32u));
+        uint32_t u0 = fsl_c(lo, hi, xsum);
+        if (xsum > 32u) u0 = shl_c(lo, xsum - 32u);   // (rare; predicated, off the common dependency chain)
         const uint32_t u1 = shl_c(u0, nbL), u2 = shl_c(u1, nbM);
         const uint32_t aL = shr_c(u0, 32u - nbL), aM = shr_c(u1, 32u - nbM), aO = shr_c(u2, 32u - nbO);
         c.eL = fse_lds16(c.qTL + (((fL << nbL) + aL) << 1));
