@@ -24,8 +24,8 @@ def raw(rep):
 
 def main(tag):
     lines = [f"# ncu summary {tag}", "", "Source: `gpurun_out/prof_<kernel>_%s.ncu-rep` (`ncu --set full --clock-control none --import-source on`, one launch per kernel," % tag,
-             "workload = bench.py config C2b, 8192 frames) and `launches_%s.csv` (`--metrics gpu__time_duration.sum`, cold-cache, serialised: compare shares)." % tag, ""]
-    for k in ["k_setup", "k_huf", "k_fse", "k_exec"]:
+             "workload = config C2b, 8192 frames, kernels launched one after the other; k_exec_cta: config C2a, 64 frames of 128 chained blocks) and `launches_%s.csv` (`--metrics gpu__time_duration.sum`, cold-cache, serialised: compare shares)." % tag, ""]
+    for k in ["k_setup", "k_huf", "k_fse", "k_exec", "k_xxh64", "k_exec_cta"]:
         try:
             m = raw(f"gpurun_out/prof_{k}_{tag}.ncu-rep")
         except Exception as e:
@@ -64,4 +64,4 @@ def main(tag):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else "r01a")
+    main(sys.argv[1] if len(sys.argv) > 1 else "r02")
