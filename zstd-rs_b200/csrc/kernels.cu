@@ -1136,30 +1136,8 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
                         for (uint32_t k = 1; k < K; k++) { co = lasts == k ? raw[3 * k] : co; cl = lasts == k ? raw[3 * k + 1] : cl; }
                         carry_out = __shfl_sync(0xffffffffu, co, lastl); carry_lit = __shfl_sync(0xffffffffu, cl, lastl);
                     }
-                    // records: two batches ahead (into L2)
-                    if (base + 2 * EXEC_BATCH < nseq_u && lane * 128u < (nseq_u - base - 2 * EXEC_BATCH) * 12u && lane * 128u < EXEC_BATCH * 12u)
-                        prefetch_l2(reinterpret_cast<const uint8_t *>(seqs + (uint64_t)(base + 2 * EXEC_BATCH) * 3) + lane * 128u);
-                    // match sources of the NEXT batch: its records are in L2 by now (requested a batch ago); their positions follow from
-                    // the prefix sums without a scan.  The DRAM round trip (~1 us: thousands of frames are live, the windows do not
-                    // stay in L2) then overlaps this whole batch instead of stalling the next batch's first rows.
-                    if (B200Z_EXEC_PREFETCH && resolved && base + EXEC_BATCH < nseq_u && avail >= min(nseq_u, base + 2 * EXEC_BATCH)) {
-                        const uint32_t nb2 = min(EXEC_BATCH, nseq_u - base - EXEC_BATCH);
-                        const uint32_t *sp2 = seqs + (uint64_t)(base + EXEC_BATCH + K * lane) * 3;
-                        uint32_t r2[3 * K];
-#pragma unroll
-                        for (uint32_t k = 0; k < 3 * K; k++) r2[k] = K * lane + k / 3 < nb2 ? ld_cg_u32(sp2 + k) : 0u;
-                        uint32_t po = __shfl_up_sync(0xffffffffu, r2[3 * (K - 1)], 1), pl = __shfl_up_sync(0xffffffffu, r2[3 * (K - 1) + 1], 1);
-                        if (lane == 0) { po = carry_out; pl = carry_lit; }
-                        const uint8_t *blk0 = out + (st.produced - old_out);   // the block's first output byte
-                        const uint64_t reach0 = st.produced - old_out - st.drained;
-#pragma unroll
-                        for (uint32_t k = 0; k < K; k++) {
-                            const uint32_t ms = po + (r2[3 * k + 1] - pl);            // match start, block-relative
-                            const uint32_t of2 = seq_sym_resolve(r2[3 * k + 2], bh0, bh1, bh2);
-                            if (K * lane + k < nb2 && of2 != 0u && (uint64_t)of2 <= reach0 + ms) prefetch_l2(blk0 + ms - of2);
-                            po = r2[3 * k]; pl = r2[3 * k + 1];
-                        }
-                    }
+                    if (base + EXEC_BATCH < nseq_u && lane * 128u < (nseq_u - base - EXEC_BATCH) * 12u && lane * 128u < EXEC_BATCH * 12u)
+                        prefetch_l2(reinterpret_cast<const uint8_t *>(seqs + (uint64_t)(base + EXEC_BATCH) * 3) + lane * 128u);
                 }
                 // the records are prefix sums already (k_fse): batch totals and batch-relative positions are differences
                 const uint32_t T = carry_out - old_out, L = carry_lit - old_lit;
