@@ -46,7 +46,7 @@ constexpr uint32_t XC_OFF_FIRST = XC_OFF_MASK + XC_MASK_BYTES;
 constexpr uint32_t XC_OFF_RING = XC_OFF_FIRST + XC_FIRST_BYTES;
 constexpr uint32_t XC_OFF_PEND = XC_OFF_RING + XC_RING * 8;   // [XC_PROWS][4] u32
 constexpr uint32_t XC_OFF_MISC = XC_OFF_PEND + XC_PROWS * 16;
-constexpr uint32_t XC_SMEM_BYTES = XC_OFF_MISC + 128;   // >= sizeof(XcMisc)
+constexpr uint32_t XC_SMEM_BYTES = XC_OFF_MISC + 128;
 static_assert(XC_SMEM_BYTES <= 232448, "k_exec_cta: more than 227 KiB of shared memory");
 static_assert(XC_MASK_BYTES >= XC_ROWS_MAX * 16 && XC_FIRST_BYTES >= XC_ROWS_MAX * 8, "k_exec_cta tables");
 constexpr uint32_t XC_SPIN_LIMIT = 1u << 18;               // bounded waits: a stuck wait turns into a bail-out, never a hang
@@ -57,7 +57,6 @@ struct XcMisc {               // at XC_OFF_MISC
     uint32_t bail;            // a thread found something this kernel does not handle (or a wait timed out)
     uint32_t ovl[4];          // per batch (mod 4): some match overlaps its own output
     uint32_t end_a[2];        // per batch (mod 2): window position where the batch's last sequence ends
-    uint32_t cur_row[XC_WARPS];   // the row each warp is working on: every row below the minimum is finished
 };
 
 // ---- PTX wrappers: mbarrier + bulk async copies (TMA, non-tensor form)
@@ -121,14 +120,9 @@ __device__ __forceinline__ uint32_t xc_lds_volatile(uint32_t a) { uint32_t v; as
 template <bool FAR, bool LITG, int NR>
 __device__ __forceinline__ bool xc_rows(const XcBlk &B, uint32_t r0, uint32_t lo_a, bool has_ovl, uint32_t lane) {
     const uint32_t S = B.S, S_mask = S + XC_OFF_MASK, S_first = S + XC_OFF_FIRST, S_ring = S + XC_OFF_RING, S_pend = S + XC_OFF_PEND;
-    const uint32_t S_cur = S + XC_OFF_MISC + (uint32_t)offsetof(XcMisc, cur_row);
-    // Which sources are certainly final: everything below the current sub-phase (lo_a), and every row below the lowest row any
-    // warp is working on (rows are handed out in increasing order: all rows below the minimum are finished).  A match byte whose
-    // source lies above that line follows its source row's pending plane; sources below woff are in earlier blocks of the frame
-    // (global memory).
-    if (lane == 0) sts32(S_cur + ((threadIdx.x >> 5) << 2), r0);
-    const uint32_t fr = __reduce_min_sync(0xffffffffu, lane < XC_WARPS ? xc_lds_volatile(S_cur + (lane << 2)) : 0xFFFFFFFFu);
-    const int32_t fin_a = (int32_t)max(max(lo_a, fr << 7), B.woff);
+    // first position of the block in this sub-phase: sources below it are final (earlier sub-phases / phases), or -- below
+    // woff -- in earlier blocks of the frame (global memory)
+    const int32_t fin_a = (int32_t)max(lo_a, B.woff);
     uint32_t a0[NR], word[NR], pend[NR];
     int32_t src[NR][4];
 #pragma unroll
@@ -157,8 +151,12 @@ __device__ __forceinline__ bool xc_rows(const XcBlk &B, uint32_t r0, uint32_t lo
                 const uint32_t kk = a - x, off = 0u - noff;
                 if (mt && kk >= off) src[j][k] = (int32_t)(x - off + kk % off);
             }
+            // A source produced in this sub-phase: its row's pending plane says whether the byte is there yet (my own row's
+            // planes are still all-ones: in-row sources always go through the rounds below).  The plane word is read for every
+            // byte (any address inside the plane area is harmless) so that there is no branch.
             const uint32_t sa = (uint32_t)src[j][k];
-            const bool wait = mt && src[j][k] >= fin_a;   // produced by a row that may still be in flight (or by this very row)
+            const uint32_t pm = xc_lds_volatile(S_pend + (((sa >> 7) & (XC_PROWS - 1u)) << 4) + ((sa & 3u) << 2));
+            const bool wait = mt && src[j][k] >= fin_a && ((pm >> ((sa >> 2) & 31u)) & 1u) != 0u;
             const bool far = FAR && mt && src[j][k] < (int32_t)B.woff;
             const bool litg = LITG && !mt;   // literals read from global memory: src = literal index + XC_LITG_BIAS
             uint32_t v = lds8(S + ((wait || far || litg) ? a : sa));   // (a byte that waits / comes from global memory reads itself: harmless)
@@ -172,24 +170,20 @@ __device__ __forceinline__ bool xc_rows(const XcBlk &B, uint32_t r0, uint32_t lo
 #pragma unroll
     for (int j = 0; j < NR; j++) { sts32(S + a0[j], word[j]); anyp = anyp || pend[j] != 0u; }
     if (__any_sync(0xffffffffu, anyp)) {
-        // Bytes whose source may not be there yet.  Publish first (data, then which bytes are still pending), then look: each round
-        // copies every pending byte whose source byte is no longer pending.  The lowest pending byte of the lowest unfinished row
-        // never depends on a pending byte, so the loops of all warps terminate.
+        // Bytes whose source was not there yet.  Each round: publish which bytes are still pending (data first, then the
+        // planes), then copy every pending byte whose source byte is no longer pending.  The lowest pending byte of the lowest
+        // unfinished row never depends on a pending byte, so the loops of all warps terminate.
         uint32_t spins = 0;
         bool publish = true;
         for (;;) {
             __syncwarp();
-            uint32_t pm[NR][4], left[NR];
+            uint32_t pm[NR][4], left = 0;
 #pragma unroll
             for (int j = 0; j < NR; j++) {
-                left[j] = 0;
 #pragma unroll
-                for (int k = 0; k < 4; k++) { pm[j][k] = __ballot_sync(0xffffffffu, (pend[j] >> k) & 1u); left[j] |= pm[j][k]; }
+                for (int k = 0; k < 4; k++) { pm[j][k] = __ballot_sync(0xffffffffu, (pend[j] >> k) & 1u); left |= pm[j][k]; }
             }
-            uint32_t all_left = 0;
-#pragma unroll
-            for (int j = 0; j < NR; j++) all_left |= left[j];
-            if (all_left == 0u) break;
+            if (left == 0u) break;
             if (publish) {
                 if (lane < 4) {
                     xc_fence_cta();
@@ -204,7 +198,6 @@ __device__ __forceinline__ bool xc_rows(const XcBlk &B, uint32_t r0, uint32_t lo
             bool changed = false;
 #pragma unroll
             for (int j = 0; j < NR; j++) {
-                if (left[j] == 0u) continue;   // (warp-uniform) nothing pending in this row any more
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const uint32_t sa = (uint32_t)src[j][k];
@@ -304,7 +297,6 @@ __device__ __forceinline__ void xc_build(const XcBlk &B, uint32_t k, uint32_t ti
 // all pending planes = "pending": done between phases (everything below the next phase's first row is final and is never looked up)
 __device__ __forceinline__ void xc_planes_reset(uint32_t S, uint32_t tid) {
     for (uint32_t j = tid; j < XC_PROWS * 4u / 2u; j += XC_THREADS) sts64(S + XC_OFF_PEND + (j << 3), 0xFFFFFFFFu, 0xFFFFFFFFu);
-    if (tid < XC_WARPS) sts32(S + XC_OFF_MISC + (uint32_t)offsetof(XcMisc, cur_row) + (tid << 2), 0u);   // "no row finished yet" for the frontier
 }
 
 __global__ void __launch_bounds__(XC_THREADS, 1) k_exec_cta(const BlockDesc *__restrict__ descs, const BlockAux *__restrict__ aux,
