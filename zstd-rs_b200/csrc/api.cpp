@@ -765,20 +765,10 @@ static int decode_frames_pipelined(b200z_ctx *c, const uint8_t *input, size_t in
     for (size_t i = 0; i < nframes; i++) total_cap += frames[i].out_cap;
     std::vector<size_t> cut(1, 0);
     {
-        // The call is PCIe-bound (the plaintext's way back): what is not hidden is the time before the first D2H can start (plan +
-        // H2D + kernels of chunk 0) and the last chunk's D2H.  So the chunks ramp up: two small ones first (1/8 and 1/4 of the
-        // nominal size: their kernels are latency-bound anyway), then nominal ones.
-        std::vector<uint64_t> bound;   // cumulative output bytes at which a chunk ends
-        const uint64_t per = total_cap / nchunks + 1;
-        uint64_t at = 0;
-        const bool ramp = nchunks >= 3 && !getenv("B200Z_PIPELINE_NO_RAMP");
-        if (ramp) { at += per / 8; bound.push_back(at); at += per / 4; bound.push_back(at); }
-        while (at + per < total_cap) { at += per; bound.push_back(at); }
-        uint64_t acc = 0;
-        size_t bi = 0;
+        uint64_t acc = 0, per = total_cap / nchunks + 1;
         for (size_t i = 0; i < nframes; i++) {
             acc += frames[i].out_cap;
-            if (bi < bound.size() && acc >= bound[bi] && i + 1 < nframes) { cut.push_back(i + 1); while (bi < bound.size() && acc >= bound[bi]) bi++; }
+            if (acc >= per * cut.size() && i + 1 < nframes && cut.size() < nchunks) cut.push_back(i + 1);
         }
         cut.push_back(nframes);
     }
