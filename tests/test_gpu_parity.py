@@ -663,3 +663,40 @@ def test_exact_path_replay_rolls_back(pkg, ctx, oracle, monkeypatch):
     raw_big = [k for k in range(nblocks) if (b.debug_block_flags(k) & 1) and len(b.debug_sequences(k)) > 1000]
     assert len(raw_big) >= 4, "no long block went through k_fse's exact path"
     b.close()
+
+
+def test_device_walk_matches_host_plan(pkg, ctx, oracle, manifest, monkeypatch):
+    """Device-resident input: k_walk follows the frame / block / section headers on the GPU and the planner works from its digests
+    (no copy of the compressed data back to the host).  Every outcome -- status, stage, sizes, bytes read, checksum, plaintext --
+    must equal what the host walk produces from the same bytes: the golden corpus, every fuzz artifact (incl. the ones without a
+    dictionary id), truncated frames, garbage."""
+    import torch
+    frames = [read_golden("decodecorpus", n) for n in sorted(manifest["corpus"])]
+    for sub, files in manifest["fuzz"].items():
+        frames += [read_golden("fuzz", sub, f) for f in files]
+    data = read_golden("decodecorpus", "z000002.zst")
+    frames += [data[:c] for c in list(range(0, 40)) + list(range(40, len(data), 53))]
+    rng = np.random.Generator(np.random.PCG64(3))
+    frames += [bytes([0x28, 0xB5, 0x2F, 0xFD]) + rng.integers(0, 256, int(n), dtype=np.uint8).tobytes() for n in rng.integers(0, 300, 40)]
+    frames = [f if len(f) else b"" for f in frames]
+    caps = [1 << 17] * len(frames)
+    for i, n in enumerate(sorted(manifest["corpus"])):
+        caps[i] = manifest["corpus"][n]["size"]
+    io, comp, total = _io(pkg, frames, caps)
+    comp = comp if len(comp) else np.zeros(1, np.uint8)
+    outs = {}
+    for mode in ("host", "device"):
+        monkeypatch.setenv("B200Z_WALK", "host" if mode == "host" else "device")
+        d_in = torch.from_numpy(comp.copy()).cuda()
+        d_out = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
+        b = pkg.Batch(ctx, d_in, io)
+        b.run(d_out)
+        outs[mode] = (b.finish().copy(), d_out.cpu().numpy(), b.info()["blocks"])
+        b.close()
+    rh, oh, nbh = outs["host"]
+    rd, od, nbd = outs["device"]
+    assert nbh == nbd and nbd > 2000
+    for k in rh.dtype.names:
+        assert np.array_equal(rh[k], rd[k]), k
+    assert np.array_equal(oh, od)
+    assert (rd["status"] == 0).sum() >= 101 and (rd["status"] != 0).sum() > 50

@@ -378,8 +378,11 @@ struct b200z_batch {
     bool checksummed = false;
 };
 
+// what k_walk brought back for a batch whose input lives in device memory (the planner then never sees the compressed bytes)
+struct WalkHost { std::vector<WalkFrame> wf; std::vector<WalkBlock> wb; std::vector<uint32_t> first; };
+
 static int plan_batch(b200z_batch *b, const uint8_t *in, size_t in_len, const b200z_frame_io *frames, size_t nframes,
-                      const b200z_dict *const *dicts, size_t ndicts, const b200z_dict *forced, uint64_t max_window) {
+                      const b200z_dict *const *dicts, size_t ndicts, const b200z_dict *forced, uint64_t max_window, const WalkHost *walk = nullptr) {
     Submission &s = b->sub;
     s.clear();
     b->info.assign(nframes, FramePlanInfo());
@@ -399,8 +402,11 @@ static int plan_batch(b200z_batch *b, const uint8_t *in, size_t in_len, const b2
         FramePlanInfo &fi = b->info[i];
         const b200z_frame_io &io = frames[i];
         if (io.src_off > in_len || io.src_size > in_len - io.src_off) { fi.pre_status = B200Z_ERR_INVALID_ARGUMENT; continue; }
-        const uint8_t *p = in + io.src_off;
+        // host input: the frame's bytes; device input: the bytes the header walk picked (frame header here, block digests below)
+        const uint8_t *p = walk ? walk->wf[i].hdr : in + io.src_off;
         size_t len = io.src_size, consumed = 0;
+        uint32_t wk = walk ? walk->first[i] : 0;   // next block digest of this frame
+        const uint32_t wk_end = walk ? wk + walk->wf[i].nblocks : 0;
         int e = parse_frame_header(p, len, fi.hdr, fi.skip_len, consumed);
         if (e) { fi.pre_status = e; fi.pre_stage = B200Z_STAGE_FRAME_HEADER; fi.bytes_read_full = consumed; continue; }
         if ((e = frame_window_size(fi.hdr, fi.window))) { fi.pre_status = e; fi.pre_stage = B200Z_STAGE_FRAME_HEADER; continue; }
@@ -430,7 +436,12 @@ static int plan_batch(b200z_batch *b, const uint8_t *in, size_t in_len, const b2
         for (;;) {
             if (len - pos < 3) { fd.host_status = mk_status(B200Z_ERR_BLOCK_HEADER_READ, B200Z_STAGE_BLOCK_HEADER); break; }
             BlockHeader bh;
-            if ((e = parse_block_header(p + pos, bh))) { fd.host_status = mk_status((uint32_t)e, B200Z_STAGE_BLOCK_HEADER); break; }
+            const WalkBlock *wbk = nullptr;
+            if (walk) {
+                if (wk >= wk_end || walk->wb[wk].pos != pos) return B200Z_ERR_INVALID_ARGUMENT;   // (the walk and the planner follow the same chain)
+                wbk = &walk->wb[wk++];
+            }
+            if ((e = parse_block_header(wbk ? wbk->bh : p + pos, bh))) { fd.host_status = mk_status((uint32_t)e, B200Z_STAGE_BLOCK_HEADER); break; }
             pos += 3;
             if (len - pos < bh.content_size) {
                 fd.host_status = mk_status(bh.type == BT_COMPRESSED ? B200Z_ERR_BLOCK_CONTENT_READ : B200Z_ERR_BLOCK_BODY_READ, B200Z_STAGE_BLOCK_BODY);
@@ -441,7 +452,10 @@ static int plan_batch(b200z_batch *b, const uint8_t *in, size_t in_len, const b2
             BlockRefs r;
             d.src_off = io.src_off + pos; d.src_size = bh.content_size; d.frame = (uint32_t)s.frames.size();
             d.btype = bh.type; d.raw_size = bh.decompressed_size; d.block_in_frame = bif++; d.last = bh.last;
-            if (bh.type == BT_COMPRESSED) plan_compressed_block(p + pos, bh.content_size, d, r, cur, s.n_huf, s.n_fse, s.lit_bytes, s.nseq);
+            if (bh.type == BT_COMPRESSED) {
+                if (wbk) plan_compressed_block_view(wbk->lit, wbk->seq, bh.content_size, d, r, cur, s.n_huf, s.n_fse, s.lit_bytes, s.nseq);
+                else plan_compressed_block(p + pos, bh.content_size, d, r, cur, s.n_huf, s.n_fse, s.lit_bytes, s.nseq);
+            }
             pos += bh.content_size;
             bytes_read += 3 + bh.content_size;
             s.descs.push_back(d); s.refs.push_back(r);
@@ -451,7 +465,9 @@ static int plan_batch(b200z_batch *b, const uint8_t *in, size_t in_len, const b2
                 if (fi.hdr.content_checksum()) {
                     if (len - pos < 4) { fd.host_status = mk_status(B200Z_ERR_FAILED_TO_READ_CHECKSUM, B200Z_STAGE_CHECKSUM); break; }
                     fi.has_checksum = true;
-                    fi.checksum = (uint32_t)p[pos] | ((uint32_t)p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16) | ((uint32_t)p[pos + 3] << 24);
+                    if (walk && (walk->wf[i].end_pos != pos || walk->wf[i].tail_avail < 4)) return B200Z_ERR_INVALID_ARGUMENT;
+                    const uint8_t *q = walk ? walk->wf[i].tail : p + pos;
+                    fi.checksum = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
                     bytes_read += 4;
                 }
                 break;
@@ -465,6 +481,38 @@ static int plan_batch(b200z_batch *b, const uint8_t *in, size_t in_len, const b2
     return 0;
 }
 
+// k_walk twice (count, fill) with a host prefix sum in between; ~16 bytes per block and 48 per frame come back
+static int device_walk(b200z_ctx *c, const uint8_t *d_input, size_t input_len, const b200z_frame_io *frames, size_t nframes, WalkHost &w) {
+    w.wf.assign(nframes, WalkFrame()); w.first.assign(nframes, 0); w.wb.clear();
+    if (!nframes) return 0;
+    std::vector<uint64_t> so(2 * nframes);
+    for (size_t i = 0; i < nframes; i++) { so[i] = frames[i].src_off; so[nframes + i] = frames[i].src_size; }
+    DevBuf d_io, d_wf, d_first, d_wb;
+    if (int e = d_io.ensure(so.size() * 8, false)) return e;
+    if (int e = d_wf.ensure(nframes * sizeof(WalkFrame), false)) return e;
+    if (int e = d_first.ensure(nframes * 4, false)) return e;
+    CU(c, cudaMemcpyAsync(d_io.p, so.data(), so.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    const uint64_t *d_off = d_io.as<uint64_t>(), *d_sz = d_off + nframes;
+    int le = launch_walk(d_input, input_len, d_off, d_sz, (uint32_t)nframes, d_wf.as<WalkFrame>(), nullptr, nullptr, 0, c->stream);
+    if (le) return c->set_cuda_err((cudaError_t)le, "k_walk");
+    CU(c, cudaMemcpyAsync(w.wf.data(), d_wf.p, nframes * sizeof(WalkFrame), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    uint64_t total = 0;
+    for (size_t i = 0; i < nframes; i++) { w.first[i] = (uint32_t)total; total += w.wf[i].nblocks; }
+    if (total > 0xFFFFFFF0ull) return B200Z_ERR_INVALID_ARGUMENT;
+    c->launches += 1;
+    if (!total) return 0;
+    w.wb.resize(total);
+    if (int e = d_wb.ensure(total * sizeof(WalkBlock), false)) return e;
+    CU(c, cudaMemcpyAsync(d_first.p, w.first.data(), nframes * 4, cudaMemcpyHostToDevice, c->stream));
+    le = launch_walk(d_input, input_len, d_off, d_sz, (uint32_t)nframes, d_wf.as<WalkFrame>(), d_first.as<uint32_t>(), d_wb.as<WalkBlock>(), 1, c->stream);
+    if (le) return c->set_cuda_err((cudaError_t)le, "k_walk");
+    CU(c, cudaMemcpyAsync(w.wb.data(), d_wb.p, total * sizeof(WalkBlock), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->launches += 1;
+    return 0;
+}
+
 extern "C" int b200z_batch_prepare(b200z_ctx *c, const uint8_t *input, size_t input_len, int input_mem, const b200z_frame_io *frames,
                                    size_t nframes, const b200z_dict *const *dicts, size_t ndicts, const b200z_dict *forced,
                                    uint64_t max_window, b200z_batch **out) {
@@ -473,16 +521,25 @@ extern "C" int b200z_batch_prepare(b200z_ctx *c, const uint8_t *input, size_t in
     if (int e = c->use()) return e;
     std::unique_ptr<b200z_batch> b(new b200z_batch());
     b->ctx = c; b->input_len = input_len;
-    std::vector<uint8_t> host_copy;
     const uint8_t *hin = input;
+    WalkHost walk;
+    std::vector<uint8_t> host_copy;
     if (input_mem == B200Z_MEM_DEVICE) {
-        // the planner walks headers on the host; a device-side frame walker is a "next" row
-        host_copy.resize(input_len);
-        if (input_len) CU(c, cudaMemcpy(host_copy.data(), input, input_len, cudaMemcpyDeviceToHost));
-        hin = host_copy.data();
+        // The input stays on the device: k_walk follows the frame / block / section headers there and brings back the ~16 bytes per
+        // block the planner parses -- not the compressed data (B200Z_WALK=host copies it back and walks on the host,
+        // for A/B tests).
         b->d_input = input;
+        const char *wm = getenv("B200Z_WALK");
+        if (wm && !strcmp(wm, "host")) {
+            host_copy.resize(input_len);
+            if (input_len) CU(c, cudaMemcpy(host_copy.data(), input, input_len, cudaMemcpyDeviceToHost));
+            hin = host_copy.data();
+        } else {
+            hin = nullptr;
+            if (int e = device_walk(c, input, input_len, frames, nframes, walk)) return e;
+        }
     }
-    if (int e = plan_batch(b.get(), hin, input_len, frames, nframes, dicts, ndicts, forced, max_window)) return e;
+    if (int e = plan_batch(b.get(), hin, input_len, frames, nframes, dicts, ndicts, forced, max_window, hin ? nullptr : (input_mem == B200Z_MEM_DEVICE ? &walk : nullptr))) return e;
     if (input_mem != B200Z_MEM_DEVICE) {
         if (int e = b->d_input_own.ensure(input_len + 16, false)) return e;
         if (input_len) CU(c, cudaMemcpyAsync(b->d_input_own.p, input, input_len, cudaMemcpyHostToDevice, c->stream));

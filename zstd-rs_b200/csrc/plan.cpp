@@ -88,6 +88,14 @@ static TabRef one_mode(uint32_t mode, TabRef cur, int32_t slot_idx) {
 
 void plan_compressed_block(const uint8_t *c, uint32_t size, BlockDesc &d, BlockRefs &r, TableCursor &cur,
                            uint32_t &n_huf_slots, uint32_t &n_fse_slots, uint64_t &lit_bytes, uint64_t &nseq_total) {
+    plan_compressed_block_view(c, nullptr, size, d, r, cur, n_huf_slots, n_fse_slots, lit_bytes, nseq_total);
+}
+
+// `c`: the first bytes of the block content (the literals section header: at most 5 are read); `seq`: the first bytes of the sequences
+// section header (at most 4 are read), or null when `c` is the whole content.  The device-side header walk (k_walk) hands over
+// exactly these bytes per block.
+void plan_compressed_block_view(const uint8_t *c, const uint8_t *seq, uint32_t size, BlockDesc &d, BlockRefs &r, TableCursor &cur,
+                                uint32_t &n_huf_slots, uint32_t &n_fse_slots, uint64_t &lit_bytes, uint64_t &nseq_total) {
     // ---- literals section header (literals_section.rs:117-223)
     if (size == 0) { d.host_status = host_status(B200Z_ERR_LITSEC_GET_BITS, B200Z_STAGE_BLOCK_BODY, 1); return; }
     uint32_t lt = c[0] & 3, sf = (c[0] >> 2) & 3, need;
@@ -119,7 +127,7 @@ void plan_compressed_block(const uint8_t *c, uint32_t size, BlockDesc &d, BlockR
         lit_bytes += ((uint64_t)regen + 31) & ~15ull;  // 16-byte aligned, >= 16 bytes of slack for vector stores
     }
     // ---- sequences section header (sequence_section.rs:108-167)
-    const uint8_t *s = c + need + upper;
+    const uint8_t *s = seq ? seq : c + need + upper;
     uint32_t rem = size - need - upper, hdr = 0, nseq = 0, modes = 0;
     bool bad = false;
     if (rem == 0) bad = true;

@@ -53,6 +53,9 @@ struct TableCursor {
 void plan_compressed_block(const uint8_t *content, uint32_t size, BlockDesc &d, BlockRefs &r, TableCursor &cur,
                            uint32_t &n_huf_slots, uint32_t &n_fse_slots, uint64_t &lit_bytes, uint64_t &nseq_total);
 
+void plan_compressed_block_view(const uint8_t *lit_hdr, const uint8_t *seq_hdr, uint32_t size, BlockDesc &d, BlockRefs &r, TableCursor &cur,
+                                uint32_t &n_huf_slots, uint32_t &n_fse_slots, uint64_t &lit_bytes, uint64_t &nseq_total);
+
 inline uint32_t host_status(uint32_t code, uint32_t stage, uint32_t pos) { return code | (stage << 16) | (pos << 24); }
 
 // XXH64 (seed 0) streaming -- the hash the reference feeds on drain (decode_buffer.rs:42,225,290,301)
