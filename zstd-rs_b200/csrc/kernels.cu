@@ -1352,10 +1352,22 @@ __global__ void k_xxh64(const FrameDesc *__restrict__ frames, FrameState *__rest
     // memory latency otherwise: 1 ms per GiB with one load in flight per lane)
     uint64_t s = 0;
     if ((((uintptr_t)q) & 7) == 0) {
-        for (; s + 16 <= nstripes; s += 16, q += 512) {
+        // software pipelined: the next 16 stripes' words are in flight while this batch goes through the (serial) rounds -- what a
+        // lone huge frame needs (four lanes cannot hide a DRAM round trip any other way), and more bytes in flight for many frames
+        if (s + 16 <= nstripes) {
             uint64_t w[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) w[i] = *reinterpret_cast<const uint64_t *>(q + 32 * i);
+            s += 16; q += 512;
+            for (; s + 16 <= nstripes; s += 16, q += 512) {
+                uint64_t n[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) n[i] = *reinterpret_cast<const uint64_t *>(q + 32 * i);
+#pragma unroll
+                for (int i = 0; i < 16; i++) { v += w[i] * P2; v = rotl64(v, 31) * P1; }
+#pragma unroll
+                for (int i = 0; i < 16; i++) w[i] = n[i];
+            }
 #pragma unroll
             for (int i = 0; i < 16; i++) { v += w[i] * P2; v = rotl64(v, 31) * P1; }
         }
