@@ -64,3 +64,33 @@ def test_product_never_references_oracle():
 def test_xxh64_host(pkg):
     assert pkg.xxh64(b"") == 0xEF46DB3751D8E999
     assert pkg.xxh64(b"Nobody inspects the spammish repetition") == 0xFBCEA83C8A378BF1
+
+
+def test_struct_layouts_match_the_binding(pkg, tmp_path):
+    """Every struct that crosses the C-ABI as an array: the header's layout (as gcc sees it) == the numpy dtype the binding
+    fills, field by field (name, offset, size)."""
+    B = pkg.binding
+    pairs = {"b200z_frame_io": B.FRAME_IO_DTYPE, "b200z_frame_result": B.FRAME_RESULT_DTYPE, "b200z_block_desc": B.BLOCK_DESC_DTYPE,
+             "b200z_block_frame": B.BLOCK_FRAME_DTYPE, "b200z_block_status": B.BLOCK_STATUS_DTYPE}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200zstd.h"', 'int main(void) {']
+    for s, dt in pairs.items():
+        lines.append(f'  printf("{s} * %zu 0\\n", sizeof({s}));')
+        for f in dt.names:
+            lines.append(f'  printf("{s} {f} %zu %zu\\n", offsetof({s}, {f}), sizeof((({s} *)0)->{f}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    seen = 0
+    for ln in subprocess.check_output([str(exe)]).decode().split("\n"):
+        if not ln:
+            continue
+        s, f, a, b = ln.split()
+        dt = pairs[s]
+        if f == "*":
+            assert dt.itemsize == int(a), s
+        else:
+            assert dt.fields[f][1] == int(a) and dt.fields[f][0].itemsize == int(b), (s, f)
+            seen += 1
+    assert seen == sum(len(dt.names) for dt in pairs.values())
