@@ -27,6 +27,9 @@ sets = {
     "c2a64": lambda: G.config_c2a(total_bytes=1 << 30, nframes=64, cache=False),
     "c3": lambda: G.config_c3(nframes=10000, cache=False),
     "c4": lambda: G.config_c4(nframes=1024, cache=False),
+    "c4_512": lambda: G.config_c4(nframes=512, cache=False),
+    "c4_2k": lambda: G.config_c4(nframes=2048, cache=False),
+    "c4_4k": lambda: G.config_c4(nframes=4096, cache=False),
     "c5": lambda: G.config_c5(nframes=20000, cache=False),
 }
 modes = os.environ.get("QUICK_MODES", "warp,cta").split(",")

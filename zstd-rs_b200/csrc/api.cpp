@@ -248,7 +248,8 @@ struct Submission {
     std::vector<CarrySet> carries;   // TabRef::CARRY idx -> device tables (dictionaries / streaming carry)
     uint32_t n_huf = 0, n_fse = 0;
     uint64_t lit_bytes = 0, nseq = 0;
-    DevBuf d_descs, d_aux, d_frames, d_states, d_huf, d_fse, d_lit, d_seq, d_sched;
+    DevBuf d_descs, d_aux, d_frames, d_states, d_huf, d_fse, d_lit, d_seq, d_sched, d_order;
+    std::vector<uint32_t> fse_order;    // PipelineArgs::fse_order (empty: descriptor order)
     std::vector<uint32_t> cta_frames;   // frames executed by k_exec_cta (the rest: k_exec, one warp per frame)
     std::vector<uint32_t> sched_image;  // host copy of the initial ticket / resume[] image (kept alive for the async upload)
 
@@ -269,20 +270,102 @@ struct Submission {
         if ((e = d_lit.ensure(lit_bytes + 64))) return e;
         if ((e = d_seq.ensure((nseq + 4) * 12))) return e;
         // which execution kernel takes a frame.  A frame's blocks are a serial chain (window + offset history): k_exec_cta puts a
-        // whole CTA on the chain (block assembled in shared memory), k_exec one warp.  Many independent single-block frames are
-        // faster with one warp each (no cross-warp dependencies, all frames in flight); a multi-block frame is ~15x faster with the
-        // CTA.  Frames with a dictionary stay with the warp kernel (dictionary reach is its exact path).
+        // whole CTA on the chain (block assembled in shared memory, ~15x faster per frame), k_exec one warp -- but k_exec keeps
+        // ~4,700 frames in flight and needs fewer instructions per byte, so it wins as soon as there are enough frames to fill
+        // the machine (measured, 1 MiB Silesia-mix frames of 8 blocks: 512 frames 4.0 ms with CTAs / 8.7 ms with warps, 2048 frames
+        // 14.3 / 10.2 ms, 4096 frames 28.0 / 12.5 ms).  Single-block frames, tiny frames and frames with a dictionary always stay
+        // with the warp kernel (dictionary reach is its exact path).  The multi-block frames are split by a cost model on
+        // their work w = sequences + compressed bytes / 16 (both known from the headers), largest first: the k largest go to
+        // k_exec_cta, the rest to k_exec, k chosen to minimise
+        //     t_cta(k) + t_warp(rest),  t_cta  = max(w of the k / SMs, largest w) * kCtaMs      (one CTA per frame, a frame at a time)
+        //                               t_warp = largest w * kWarpChainMs + w of the rest * kWarpMs   (the longest chain, slowed
+        //                                        down by everything else in flight: 8.7 / 10.2 / 12.5 ms above)
+        // (the two kernels run one after the other: each wants whole SMs).  Constants fitted to the measurements above and to
+        // 64 chained 16 MiB text frames (17.4 ms with CTAs); the crossover for 1 MiB frames is ~1,400 frames.
         // B200Z_EXEC_MODE = warp | cta | auto (default) overrides for tests and measurements.
         cta_frames.clear();
         {
             const char *m = getenv("B200Z_EXEC_MODE");
             const bool force_warp = m && !strcmp(m, "warp"), force_cta = m && !strcmp(m, "cta");
+            std::vector<std::pair<uint64_t, uint32_t>> cand;   // (work, frame)
+            uint64_t warp_only_work = 0;
             for (size_t f = 0; f < frames.size() && !force_warp; f++) {
                 const FrameDesc &fd = frames[f];
-                if (fd.dict || fd.nblocks == 0) continue;
-                uint64_t src = 0;
-                for (uint32_t k = 0; k < fd.nblocks; k++) src += descs[fd.first_block + k].src_size;
-                if (force_cta || (fd.nblocks >= 2 && src >= 4096)) cta_frames.push_back((uint32_t)f);
+                if (fd.nblocks == 0) continue;
+                uint64_t src = 0, nseq = 0;
+                for (uint32_t k = 0; k < fd.nblocks; k++) { src += descs[fd.first_block + k].src_size; nseq += descs[fd.first_block + k].nseq; }
+                const uint64_t w = nseq + src / 16;
+                if (fd.dict) { warp_only_work += w; continue; }
+                if (force_cta) cta_frames.push_back((uint32_t)f);
+                else if (fd.nblocks >= 2 && src >= 4096) cand.emplace_back(w, (uint32_t)f);
+                else warp_only_work += w;
+            }
+            if (!cand.empty()) {
+                constexpr double kCtaMs = 1.06e-5, kWarpChainMs = 5.8e-5, kWarpMs = 1.07e-8;
+                const double sms = (double)std::max<uint32_t>(1u, num_sms());
+                std::sort(cand.begin(), cand.end(), [](const auto &x, const auto &y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
+                std::vector<uint64_t> suffix(cand.size() + 1, 0);
+                for (size_t i = cand.size(); i-- > 0;) suffix[i] = suffix[i + 1] + cand[i].first;
+                size_t best_k = 0;
+                double best_t = 0, t_none = 0, t_all = 0;
+                uint64_t prefix = 0;
+                for (size_t k = 0; k <= cand.size(); k++) {   // the k largest on CTAs
+                    const double t_cta = k ? std::max((double)prefix / sms, (double)cand[0].first) * kCtaMs : 0.0;
+                    const double t_warp = (k < cand.size() ? (double)cand[k].first * kWarpChainMs : 0.0) + (double)(suffix[k] + warp_only_work) * kWarpMs;
+                    if (k == 0) t_none = t_cta + t_warp;
+                    if (k == cand.size()) t_all = t_cta + t_warp;
+                    if (k == 0 || t_cta + t_warp < best_t) { best_t = t_cta + t_warp; best_k = k; }
+                    if (k < cand.size()) prefix += cand[k].first;
+                }
+                // a split only when the model promises a clear gain over both pure choices (measured on 4096 similar frames: moving
+                // the 171 largest to CTAs shortened k_exec by 0.9 ms and cost 2.4 ms of k_exec_cta)
+                if (best_k != 0 && best_k != cand.size() && best_t > 0.7 * std::min(t_none, t_all)) best_k = t_none <= t_all ? 0 : cand.size();
+                for (size_t k = 0; k < best_k; k++) cta_frames.push_back(cand[k].second);   // largest first: the ticket order of k_exec_cta
+            }
+        }
+        // The order in which k_fse takes the blocks.  k_exec runs beside k_fse and walks every frame's blocks in order: with the
+        // descriptor order (frame after frame) the frames at the end of the list sit idle until k_fse's last wave, and then have their
+        // whole chain still to run (4096 x 8 blocks: the pair took k_fse + k_exec, 18.8 ms).  Block-major order -- block 0 of every
+        // frame, then block 1, ... -- keeps k_fse ahead of every chain.  Blocks of k_exec_cta's frames (which start when k_fse is
+        // complete) come last.  B200Z_FSE_ORDER=0 keeps the descriptor order.
+        fse_order.clear();
+        {
+            const char *eo = getenv("B200Z_FSE_ORDER");
+            std::vector<uint8_t> on_cta(frames.size(), 0);
+            for (uint32_t f : cta_frames) on_cta[f] = 1;
+            uint32_t maxb = 0;
+            size_t covered = 0;
+            bool want = false;
+            for (size_t f = 0; f < frames.size(); f++) {
+                covered += frames[f].nblocks;
+                if (on_cta[f]) continue;
+                maxb = std::max(maxb, frames[f].nblocks);
+                if (frames[f].nblocks >= 2) want = true;
+            }
+            if (want && covered == descs.size() && !(eo && eo[0] == '0')) {
+                std::vector<uint32_t> start(maxb + 2, 0);   // start[bi + 1] = blocks with block-in-frame index bi among the warp kernel's frames
+                for (size_t f = 0; f < frames.size(); f++)
+                    if (!on_cta[f]) for (uint32_t k = 0; k < frames[f].nblocks; k++) start[k + 1]++;
+                for (uint32_t k = 0; k <= maxb; k++) start[k + 1] += start[k];
+                uint32_t tail = start[maxb + 1];   // k_exec_cta's frames follow, frame after frame
+                fse_order.assign(descs.size(), 0u);
+                for (size_t f = 0; f < frames.size(); f++)
+                    for (uint32_t k = 0; k < frames[f].nblocks; k++) {
+                        if (on_cta[f]) fse_order[tail++] = frames[f].first_block + k;
+                        else fse_order[start[k]++] = frames[f].first_block + k;
+                    }
+                // inside a row: by sequence count, so that the 16 chains of a k_fse warp have similar lengths (a warp takes as long as
+                // its longest chain) and the longest chains start first
+                {
+                    uint32_t lo = 0;
+                    for (uint32_t k = 0; k < maxb; k++) {
+                        const uint32_t hi = start[k];   // (start[k] has advanced to the end of row k)
+                        std::sort(fse_order.begin() + lo, fse_order.begin() + hi,
+                                  [&](uint32_t x, uint32_t y) { return descs[x].nseq != descs[y].nseq ? descs[x].nseq > descs[y].nseq : x < y; });
+                        lo = hi;
+                    }
+                }
+                if ((e = d_order.ensure(4 * fse_order.size()))) return e;
             }
         }
         // scheduling buffer: [ticket + 3 counters][resume[nframes]][cta frame list][initial image of the first two parts]
@@ -312,6 +395,7 @@ struct Submission {
         if (!descs.empty()) CU(c, cudaMemcpyAsync(d_descs.p, descs.data(), descs.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice, stream));
         if (!frames.empty()) CU(c, cudaMemcpyAsync(d_frames.p, frames.data(), frames.size() * sizeof(FrameDesc), cudaMemcpyHostToDevice, stream));
         if (!states.empty()) CU(c, cudaMemcpyAsync(d_states.p, states.data(), states.size() * sizeof(FrameState), cudaMemcpyHostToDevice, stream));
+        if (!fse_order.empty()) CU(c, cudaMemcpyAsync(d_order.p, fse_order.data(), 4 * fse_order.size(), cudaMemcpyHostToDevice, stream));
         if (!cta_frames.empty())
             CU(c, cudaMemcpyAsync(d_sched.as<uint8_t>() + 16 + 4 * frames.size(), cta_frames.data(), 4 * cta_frames.size(), cudaMemcpyHostToDevice, stream));
         if (!frames.empty()) {
@@ -330,6 +414,7 @@ struct Submission {
         a.ticket = (uint32_t *)sp; a.resume = (uint32_t *)(sp + 16); a.cta_frames = (const uint32_t *)(sp + 16 + 4 * frames.size());
         a.n_cta_frames = (uint32_t)cta_frames.size(); a.sched_bytes = (uint32_t)(16 + 4 * frames.size());
         a.sched_init = (const uint32_t *)(sp + 16 + 4 * (frames.size() + cta_frames.size()));
+        a.fse_order = fse_order.empty() ? nullptr : d_order.as<uint32_t>();
         return a;
     }
 };

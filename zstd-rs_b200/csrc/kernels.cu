@@ -674,7 +674,7 @@ __device__ __noinline__ void fse_exact_block(const BlockDesc *d, BlockAux *aux, 
 }
 
 __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs, BlockAux *__restrict__ aux, const uint8_t *__restrict__ input,
-                                          uint32_t *__restrict__ seq_scratch, uint32_t nblocks) {
+                                          uint32_t *__restrict__ seq_scratch, uint32_t nblocks, const uint32_t *__restrict__ order) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // this CTA is resident: k_exec may follow (launch_pipeline_overlapped)
     extern __shared__ __align__(16) uint8_t smem_fse[];
     uint16_t *tabs = reinterpret_cast<uint16_t *>(smem_fse);
@@ -695,6 +695,7 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
         FseChain &c = ch[k];
         c.b = blockIdx.x * FSE_BLOCKS_PER_CTA + FSE_CHAINS * lane + k;   // neighbouring blocks share a lane: similar lengths
         c.active = lane < FSE_LANES && c.b < nblocks;
+        if (c.active && order) c.b = order[c.b];   // PipelineArgs::fse_order
         c.d = c.active ? &descs[c.b] : nullptr;
         c.st_seq = 0; c.run = false; c.bad = false;
         if (c.active) {
@@ -1544,7 +1545,7 @@ int init_kernels() {
     return 0;
 }
 
-static uint32_t num_sms() {
+uint32_t num_sms() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || g_num_sms[dev] <= 0) return 148;
     return (uint32_t)g_num_sms[dev];
@@ -1566,7 +1567,7 @@ int launch_stage(const PipelineArgs &a, int stage, cudaStream_t s) {
                 // through a shared-memory queue (k_fse2) -- measured slower on B200 (1.34 vs 1.13 ms on C2b: the chain only drops to
                 // 92 instructions and pays for the queue hand-off), kept for A/B runs.
                 static const bool one_warp = [] { const char *e = getenv("B200Z_FSE"); return !(e && e[0] == '2'); }();
-                if (one_warp) k_fse<<<cdiv(a.nblocks, FSE_BLOCKS_PER_CTA), 32, kFseSmem, s>>>(a.descs, a.aux, a.input, a.seq_scratch, a.nblocks);
+                if (one_warp) k_fse<<<cdiv(a.nblocks, FSE_BLOCKS_PER_CTA), 32, kFseSmem, s>>>(a.descs, a.aux, a.input, a.seq_scratch, a.nblocks, a.fse_order);
                 else k_fse2<<<cdiv(a.nblocks, F2_LANES), 64, kFse2Smem, s>>>(a.descs, a.aux, a.input, a.seq_scratch, a.nblocks);
             }
             break;
