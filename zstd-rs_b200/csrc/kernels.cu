@@ -673,9 +673,27 @@ __device__ __noinline__ void fse_exact_block(const BlockDesc *d, BlockAux *aux, 
     aux[b].out_size = (ovf >> 31) ? 0xffffffffu : out_end - lit_end + d->regen_size;   // sum of ml + regenerated literals
 }
 
+#ifdef B200Z_PROBE
+// Development probe (profiles/variants.sh probe "-DB200Z_PROBE", profiles/probe_overlap.py): device timestamps of the k_fse / k_exec pair.
+// [0] first k_fse CTA start, [1] last k_fse CTA end, [2] first k_exec warp start, [3] last k_exec warp end, [4] last k_exec warp start,
+// [5] first k_exec warp end (globaltimer, ns).  Not part of the shipped library.
+__device__ unsigned long long g_probe[8];
+__device__ __forceinline__ unsigned long long probe_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+extern "C" int b200z_probe_read(unsigned long long *out, int reset) {
+    if (out && cudaMemcpyFromSymbol(out, g_probe, sizeof(unsigned long long) * 8) != cudaSuccess) return 1;
+    if (reset) {
+        const unsigned long long init[8] = {~0ull, 0, ~0ull, 0, 0, ~0ull, 0, 0};
+        if (cudaMemcpyToSymbol(g_probe, init, sizeof init) != cudaSuccess) return 1;
+    }
+    return 0;
+}
+#endif
 __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs, BlockAux *__restrict__ aux, const uint8_t *__restrict__ input,
                                           uint32_t *__restrict__ seq_scratch, uint32_t nblocks, const uint32_t *__restrict__ order) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // this CTA is resident: k_exec may follow (launch_pipeline_overlapped)
+#ifdef B200Z_PROBE
+    if (threadIdx.x == 0) atomicMin(&g_probe[0], probe_now());
+#endif
     extern __shared__ __align__(16) uint8_t smem_fse[];
     uint16_t *tabs = reinterpret_cast<uint16_t *>(smem_fse);
     uint32_t *s_ll_base = reinterpret_cast<uint32_t *>(smem_fse + FSE_BLOCKS_PER_CTA * FSE_TAB_U16 * 2);
@@ -838,6 +856,9 @@ __global__ void __launch_bounds__(32) k_fse(const BlockDesc *__restrict__ descs,
 #pragma unroll
     for (int k = 0; k < (int)FSE_CHAINS; k++)
         if (ch[k].active) fse_publish_ready(aux, ch[k].b);
+#ifdef B200Z_PROBE
+    if (threadIdx.x == 0) atomicMax(&g_probe[1], probe_now());
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1001,6 +1022,9 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
     const uint32_t f = frame_base + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const uint32_t lane = threadIdx.x & 31, lt = lanemask_lt();
     if (f >= nframes) return;
+#ifdef B200Z_PROBE
+    if (lane == 0) { const unsigned long long t = probe_now(); atomicMin(&g_probe[2], t); atomicMax(&g_probe[4], t); }
+#endif
     uint32_t a_mask = (uint32_t)__cvta_generic_to_shared(s_mask[threadIdx.x >> 5]);   // this warp's bitmask of sequence ends
     uint32_t a_recs = (uint32_t)__cvta_generic_to_shared(s_recs[threadIdx.x >> 5]);   // this warp's per-sequence records
     asm volatile("" : "+r"(a_mask), "+r"(a_recs));   // keep both addresses in registers (ptxas would recompute them from %tid per chunk)
@@ -1320,6 +1344,9 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, B200Z_EXEC_MINB) k_exec(const
         o.hist[0] = st.h0; o.hist[1] = st.h1; o.hist[2] = st.h2;
         o.status = status; o.produced = st.produced; o.counter = st.counter; o.error_block = err_block; o.blocks_done = blocks_done;
         if (resume) resume[f] = RESUME_SKIP;   // a later launch of this kernel in the same pass has nothing to do here
+#ifdef B200Z_PROBE
+        { const unsigned long long t = probe_now(); atomicMax(&g_probe[3], t); atomicMin(&g_probe[5], t); }
+#endif
     }
 }
 
@@ -1625,7 +1652,8 @@ static int launch_exec_warp(const PipelineArgs &a, cudaStream_t s, bool dependen
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = dependent_of_fse ? 1 : 0;
+    static const bool no_pdl = [] { const char *e = getenv("B200Z_EXEC_PDL"); return e && e[0] == '0'; }();   // A/B knob: k_exec strictly after k_fse
+    cfg.attrs = attr; cfg.numAttrs = dependent_of_fse && !no_pdl ? 1 : 0;
     return (int)cudaLaunchKernelEx(&cfg, k_exec, a.descs, (const BlockAux *)a.aux, a.frames, a.states, a.input, (const uint8_t *)a.lit_scratch,
                                    (const uint32_t *)a.seq_scratch, a.output, a.output_cap, a.nframes, a.resume, 0u);
 }
