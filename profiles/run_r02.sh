@@ -16,6 +16,13 @@ for K in k_exec k_fse k_huf k_setup k_xxh64; do
 done
 QUICK_MODES=auto ncu --set full --clock-control none --import-source on -k regex:"k_exec_cta\$" -s 2 -c 1 -f -o gpurun_out/prof_k_exec_cta_${TAG} \
     python profiles/quick2.py c2a64 > gpurun_out/ncu_k_exec_cta_${TAG}.log 2>&1
+# where k_exec sits in time relative to k_fse (device timestamps; needs profiles/variants.sh probe "-DB200Z_PROBE" built beforehand)
+if [ -f zstd-rs_b200/variants/libb200zstd_probe.so ]; then
+  for P in 1 0; do
+    B200Z_EXEC_PDL=$P B200Z_LIB=$PWD/zstd-rs_b200/variants/libb200zstd_probe.so python profiles/probe_overlap.py c2b 2>&1 | tail -1 | sed "s/^/PDL=$P /" >> gpurun_out/probe_${TAG}.txt
+  done
+  B200Z_LIB=$PWD/zstd-rs_b200/variants/libb200zstd_probe.so python profiles/probe_overlap.py c4_4k 2>&1 | tail -1 >> gpurun_out/probe_${TAG}.txt
+fi
 for C in c2a c3 c4 c5; do
   python bench.py --config $C --skip-cpu --e2e-steps 2 --steps 5 >> gpurun_out/configs_${TAG}.jsonl 2>> gpurun_out/bench_${TAG}.err
 done
