@@ -449,11 +449,12 @@ def main():
         peak, peak_src = measured_peak()
         # roofline of THIS rank's pass (per-GPU quantity): algorithmic bytes of the rank's frames over the rank's pass time
         achieved = (fs.C + fs.D) / (M["ms"] / args.steps * 1e-3) / GB
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("pipeline_dram_bytes_per_step")
-        except Exception:
-            pass
+        traffic = None   # ncu DRAM bytes of one pass: captured for the C2b workload on one GPU only (profiles/traffic.py)
+        if args.config == "c2b" and fs.nframes == 8192:
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("pipeline_dram_bytes_per_step")
+            except Exception:
+                pass
         cfg = workload_config(args, fs_all)   # identical in both arms
         run = {"frames_per_gpu": fs.nframes, "D_bytes_per_gpu": fs.D, "C_bytes_per_gpu": fs.C, "blocks_per_gpu": M["info"]["blocks"],
                "sequences_per_gpu": M["info"]["sequences"],
