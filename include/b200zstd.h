@@ -260,6 +260,14 @@ int b200z_batch_debug_block_flags(b200z_batch *b, uint32_t block, uint32_t *flag
 /* execution scheduling counters of the last run (tests / profiling): [0] frames given to k_exec_cta (block assembled in
  * shared memory), [1] frames it handed back to k_exec (one warp per frame), [2] OR of the reasons, [3] blocks handed back */
 int b200z_batch_debug_sched(b200z_batch *b, uint32_t out[4]);
+/* Host-only views of a submission's scheduling decisions (no context, no device; for CPU tests of the host logic).
+ * b200z_debug_route_frames: which frames k_exec_cta would take (largest first) given each frame's work (sequences + compressed
+ * bytes / 16) and whether it is eligible (>= 2 blocks, >= 4096 compressed bytes, no dictionary); cta_frames has room for nframes.
+ * b200z_debug_fse_order: the order in which k_fse takes the blocks (row by row across the warp kernel's frames, by decreasing
+ * sequence count inside a row, k_exec_cta's frames last); *n_order = 0 means descriptor order; order has room for nblocks_total. */
+int b200z_debug_route_frames(const uint64_t *work, const uint8_t *eligible, size_t nframes, uint32_t sms, uint32_t *cta_frames, size_t *n_cta);
+int b200z_debug_fse_order(const uint32_t *first_block, const uint32_t *nblocks, const uint8_t *on_cta, size_t nframes, const uint32_t *nseq,
+                          size_t nblocks_total, uint32_t *order, size_t *n_order);
 void b200z_batch_destroy(b200z_batch *b);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -108,6 +108,8 @@ def lib():
         "b200z_batch_debug_sequences": (C.c_int, [vp, C.c_uint32, vp, sz, C.POINTER(sz)]),
         "b200z_batch_debug_block_flags": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_uint32)]),
         "b200z_batch_debug_sched": (C.c_int, [vp, C.POINTER(C.c_uint32)]),
+        "b200z_debug_route_frames": (C.c_int, [vp, vp, sz, C.c_uint32, vp, C.POINTER(sz)]),
+        "b200z_debug_fse_order": (C.c_int, [vp, vp, vp, sz, vp, sz, vp, C.POINTER(sz)]),
         "b200z_batch_destroy": (None, [vp]),
         "b200z_frame_decoder_new": (C.c_int, [vp, pp]),
         "b200z_frame_decoder_free": (None, [vp]),
@@ -173,6 +175,32 @@ class B200ZError(Exception):
 def xxh64(data):
     b = bytes(data)
     return lib().b200z_xxh64(b, len(b))
+
+
+def route_frames(work, eligible, sms=148):
+    """Host-only: the frames k_exec_cta would take (largest first) -- route_exec_frames, csrc/plan.cpp."""
+    w = np.ascontiguousarray(work, dtype=np.uint64)
+    el = np.ascontiguousarray(eligible, dtype=np.uint8)
+    out = np.zeros(max(len(w), 1), dtype=np.uint32)
+    n = C.c_size_t()
+    rc = lib().b200z_debug_route_frames(w.ctypes.data, el.ctypes.data, len(w), sms, out.ctypes.data, C.byref(n))
+    if rc:
+        raise B200ZError(rc, 0, "b200z_debug_route_frames")
+    return out[:n.value].copy()
+
+
+def fse_order(first_block, nblocks, on_cta, nseq):
+    """Host-only: the order in which k_fse takes the blocks (empty = descriptor order) -- build_fse_order, csrc/plan.cpp."""
+    fb = np.ascontiguousarray(first_block, dtype=np.uint32)
+    nb = np.ascontiguousarray(nblocks, dtype=np.uint32)
+    oc = np.ascontiguousarray(on_cta, dtype=np.uint8)
+    ns = np.ascontiguousarray(nseq, dtype=np.uint32)
+    out = np.zeros(max(len(ns), 1), dtype=np.uint32)
+    n = C.c_size_t()
+    rc = lib().b200z_debug_fse_order(fb.ctypes.data, nb.ctypes.data, oc.ctypes.data, len(fb), ns.ctypes.data, len(ns), out.ctypes.data, C.byref(n))
+    if rc:
+        raise B200ZError(rc, 0, "b200z_debug_fse_order")
+    return out[:n.value].copy()
 
 
 def _ptr(x):

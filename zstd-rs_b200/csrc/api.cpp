@@ -269,104 +269,41 @@ struct Submission {
         if ((e = d_fse.ensure((size_t)n_fse * sizeof(FseSlot)))) return e;
         if ((e = d_lit.ensure(lit_bytes + 64))) return e;
         if ((e = d_seq.ensure((nseq + 4) * 12))) return e;
-        // which execution kernel takes a frame.  A frame's blocks are a serial chain (window + offset history): k_exec_cta puts a
-        // whole CTA on the chain (block assembled in shared memory, ~15x faster per frame), k_exec one warp -- but k_exec keeps
-        // ~4,700 frames in flight and needs fewer instructions per byte, so it wins as soon as there are enough frames to fill
-        // the machine (measured, 1 MiB Silesia-mix frames of 8 blocks: 512 frames 4.0 ms with CTAs / 8.7 ms with warps, 2048 frames
-        // 14.3 / 10.2 ms, 4096 frames 28.0 / 12.5 ms).  Single-block frames, tiny frames and frames with a dictionary always stay
-        // with the warp kernel (dictionary reach is its exact path).  The multi-block frames are split by a cost model on
-        // their work w = sequences + compressed bytes / 16 (both known from the headers), largest first: the k largest go to
-        // k_exec_cta, the rest to k_exec, k chosen to minimise
-        //     t_cta(k) + t_warp(rest),  t_cta  = max(w of the k / SMs, largest w) * kCtaMs      (one CTA per frame, a frame at a time)
-        //                               t_warp = largest w * kWarpChainMs + w of the rest * kWarpMs   (the longest chain, slowed
-        //                                        down by everything else in flight: 8.7 / 10.2 / 12.5 ms above)
-        // (the two kernels run one after the other: each wants whole SMs).  Constants fitted to the measurements above and to
-        // 64 chained 16 MiB text frames (17.4 ms with CTAs); the crossover for 1 MiB frames is ~1,400 frames.
-        // B200Z_EXEC_MODE = warp | cta | auto (default) overrides for tests and measurements.
+        // which execution kernel takes a frame (route_exec_frames, plan.cpp): single-block frames, tiny frames and frames with a
+        // dictionary always stay with the warp kernel (dictionary reach is its exact path); the multi-block frames go to k_exec_cta
+        // or k_exec by a cost model on sequences + compressed bytes.  B200Z_EXEC_MODE = warp | cta | auto (default) overrides for
+        // tests and measurements.
         cta_frames.clear();
         {
             const char *m = getenv("B200Z_EXEC_MODE");
             const bool force_warp = m && !strcmp(m, "warp"), force_cta = m && !strcmp(m, "cta");
-            std::vector<std::pair<uint64_t, uint32_t>> cand;   // (work, frame)
-            uint64_t warp_only_work = 0;
+            std::vector<uint64_t> work(frames.size(), 0);
+            std::vector<uint8_t> eligible(frames.size(), 0);
             for (size_t f = 0; f < frames.size() && !force_warp; f++) {
                 const FrameDesc &fd = frames[f];
                 if (fd.nblocks == 0) continue;
                 uint64_t src = 0, nseq = 0;
                 for (uint32_t k = 0; k < fd.nblocks; k++) { src += descs[fd.first_block + k].src_size; nseq += descs[fd.first_block + k].nseq; }
-                const uint64_t w = nseq + src / 16;
-                if (fd.dict) { warp_only_work += w; continue; }
+                work[f] = nseq + src / 16;
+                if (fd.dict) continue;
                 if (force_cta) cta_frames.push_back((uint32_t)f);
-                else if (fd.nblocks >= 2 && src >= 4096) cand.emplace_back(w, (uint32_t)f);
-                else warp_only_work += w;
+                else eligible[f] = fd.nblocks >= 2 && src >= 4096;
             }
-            if (!cand.empty()) {
-                constexpr double kCtaMs = 1.06e-5, kWarpChainMs = 5.8e-5, kWarpMs = 1.07e-8;
-                const double sms = (double)std::max<uint32_t>(1u, num_sms());
-                std::sort(cand.begin(), cand.end(), [](const auto &x, const auto &y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
-                std::vector<uint64_t> suffix(cand.size() + 1, 0);
-                for (size_t i = cand.size(); i-- > 0;) suffix[i] = suffix[i + 1] + cand[i].first;
-                size_t best_k = 0;
-                double best_t = 0, t_none = 0, t_all = 0;
-                uint64_t prefix = 0;
-                for (size_t k = 0; k <= cand.size(); k++) {   // the k largest on CTAs
-                    const double t_cta = k ? std::max((double)prefix / sms, (double)cand[0].first) * kCtaMs : 0.0;
-                    const double t_warp = (k < cand.size() ? (double)cand[k].first * kWarpChainMs : 0.0) + (double)(suffix[k] + warp_only_work) * kWarpMs;
-                    if (k == 0) t_none = t_cta + t_warp;
-                    if (k == cand.size()) t_all = t_cta + t_warp;
-                    if (k == 0 || t_cta + t_warp < best_t) { best_t = t_cta + t_warp; best_k = k; }
-                    if (k < cand.size()) prefix += cand[k].first;
-                }
-                // a split only when the model promises a clear gain over both pure choices (measured on 4096 similar frames: moving
-                // the 171 largest to CTAs shortened k_exec by 0.9 ms and cost 2.4 ms of k_exec_cta)
-                if (best_k != 0 && best_k != cand.size() && best_t > 0.7 * std::min(t_none, t_all)) best_k = t_none <= t_all ? 0 : cand.size();
-                for (size_t k = 0; k < best_k; k++) cta_frames.push_back(cand[k].second);   // largest first: the ticket order of k_exec_cta
-            }
+            if (!force_warp && !force_cta) route_exec_frames(work.data(), eligible.data(), frames.size(), num_sms(), cta_frames);
         }
-        // The order in which k_fse takes the blocks.  k_exec runs beside k_fse and walks every frame's blocks in order: with the
-        // descriptor order (frame after frame) the frames at the end of the list sit idle until k_fse's last wave, and then have their
-        // whole chain still to run (4096 x 8 blocks: the pair took k_fse + k_exec, 18.8 ms).  Block-major order -- block 0 of every
-        // frame, then block 1, ... -- keeps k_fse ahead of every chain.  Blocks of k_exec_cta's frames (which start when k_fse is
-        // complete) come last.  B200Z_FSE_ORDER=0 keeps the descriptor order.
+        // the order in which k_fse takes the blocks (build_fse_order, plan.cpp).  B200Z_FSE_ORDER=0 keeps the descriptor order.
         fse_order.clear();
         {
             const char *eo = getenv("B200Z_FSE_ORDER");
-            std::vector<uint8_t> on_cta(frames.size(), 0);
-            for (uint32_t f : cta_frames) on_cta[f] = 1;
-            uint32_t maxb = 0;
-            size_t covered = 0;
-            bool want = false;
-            for (size_t f = 0; f < frames.size(); f++) {
-                covered += frames[f].nblocks;
-                if (on_cta[f]) continue;
-                maxb = std::max(maxb, frames[f].nblocks);
-                if (frames[f].nblocks >= 2) want = true;
+            if (!(eo && eo[0] == '0') && !frames.empty()) {
+                std::vector<uint8_t> on_cta(frames.size(), 0);
+                for (uint32_t f : cta_frames) on_cta[f] = 1;
+                std::vector<uint32_t> fb(frames.size()), nb(frames.size()), nseq(descs.size());
+                for (size_t f = 0; f < frames.size(); f++) { fb[f] = frames[f].first_block; nb[f] = frames[f].nblocks; }
+                for (size_t i = 0; i < descs.size(); i++) nseq[i] = descs[i].nseq;
+                build_fse_order(fb.data(), nb.data(), on_cta.data(), frames.size(), nseq.data(), descs.size(), fse_order);
             }
-            if (want && covered == descs.size() && !(eo && eo[0] == '0')) {
-                std::vector<uint32_t> start(maxb + 2, 0);   // start[bi + 1] = blocks with block-in-frame index bi among the warp kernel's frames
-                for (size_t f = 0; f < frames.size(); f++)
-                    if (!on_cta[f]) for (uint32_t k = 0; k < frames[f].nblocks; k++) start[k + 1]++;
-                for (uint32_t k = 0; k <= maxb; k++) start[k + 1] += start[k];
-                uint32_t tail = start[maxb + 1];   // k_exec_cta's frames follow, frame after frame
-                fse_order.assign(descs.size(), 0u);
-                for (size_t f = 0; f < frames.size(); f++)
-                    for (uint32_t k = 0; k < frames[f].nblocks; k++) {
-                        if (on_cta[f]) fse_order[tail++] = frames[f].first_block + k;
-                        else fse_order[start[k]++] = frames[f].first_block + k;
-                    }
-                // inside a row: by sequence count, so that the 16 chains of a k_fse warp have similar lengths (a warp takes as long as
-                // its longest chain) and the longest chains start first
-                {
-                    uint32_t lo = 0;
-                    for (uint32_t k = 0; k < maxb; k++) {
-                        const uint32_t hi = start[k];   // (start[k] has advanced to the end of row k)
-                        std::sort(fse_order.begin() + lo, fse_order.begin() + hi,
-                                  [&](uint32_t x, uint32_t y) { return descs[x].nseq != descs[y].nseq ? descs[x].nseq > descs[y].nseq : x < y; });
-                        lo = hi;
-                    }
-                }
-                if ((e = d_order.ensure(4 * fse_order.size()))) return e;
-            }
+            if (!fse_order.empty() && (e = d_order.ensure(4 * fse_order.size()))) return e;
         }
         // scheduling buffer: [ticket + 3 counters][resume[nframes]][cta frame list][initial image of the first two parts]
         if ((e = d_sched.ensure(2 * (16 + 4 * frames.size()) + 4 * cta_frames.size() + 32))) return e;
@@ -715,6 +652,25 @@ extern "C" int b200z_batch_run_timeline(b200z_batch *b, uint8_t *d_output, size_
     CU(c, cudaStreamSynchronize(c->stream));
     for (int i = 0; i < 4; i++) CU(c, cudaEventElapsedTime(&out_ms[i], ev[0], ev[i + 1]));
     for (auto &e : ev) cudaEventDestroy(e);
+    return 0;
+}
+// host-only views of the scheduling decisions (plan.cpp), for CPU tests: no context, no device
+extern "C" int b200z_debug_route_frames(const uint64_t *work, const uint8_t *eligible, size_t nframes, uint32_t sms, uint32_t *cta_frames, size_t *n_cta) {
+    if ((!work || !eligible) && nframes) return B200Z_ERR_INVALID_ARGUMENT;
+    if (!n_cta) return B200Z_ERR_INVALID_ARGUMENT;
+    std::vector<uint32_t> out;
+    route_exec_frames(work, eligible, nframes, sms, out);
+    if (cta_frames) for (size_t i = 0; i < out.size(); i++) cta_frames[i] = out[i];   // room for nframes entries
+    *n_cta = out.size();
+    return 0;
+}
+extern "C" int b200z_debug_fse_order(const uint32_t *first_block, const uint32_t *nblocks, const uint8_t *on_cta, size_t nframes, const uint32_t *nseq,
+                                     size_t nblocks_total, uint32_t *order, size_t *n_order) {
+    if (!n_order || ((!first_block || !nblocks || !on_cta) && nframes) || (!nseq && nblocks_total)) return B200Z_ERR_INVALID_ARGUMENT;
+    std::vector<uint32_t> out;
+    build_fse_order(first_block, nblocks, on_cta, nframes, nseq, nblocks_total, out);
+    if (order) for (size_t i = 0; i < out.size(); i++) order[i] = out[i];   // room for nblocks_total entries
+    *n_order = out.size();
     return 0;
 }
 extern "C" int b200z_num_stages(void) { return kNumStages; }

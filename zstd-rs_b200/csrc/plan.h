@@ -56,6 +56,17 @@ void plan_compressed_block(const uint8_t *content, uint32_t size, BlockDesc &d, 
 void plan_compressed_block_view(const uint8_t *lit_hdr, const uint8_t *seq_hdr, uint32_t size, BlockDesc &d, BlockRefs &r, TableCursor &cur,
                                 uint32_t &n_huf_slots, uint32_t &n_fse_slots, uint64_t &lit_bytes, uint64_t &nseq_total);
 
+// ---- scheduling decisions of a submission (pure host logic; CPU tests call them through b200z_debug_route_frames / _fse_order)
+// Which execution kernel takes a frame.  work[f] = sequences + compressed bytes / 16 of frame f, eligible[f] = the frame may go to
+// k_exec_cta (two or more blocks, >= 4096 compressed bytes, no dictionary); the others always take k_exec and only add to the
+// load.  Returns the frames of k_exec_cta, largest first (its ticket order).  The cost model and its constants: DESIGN.md 4.1.
+void route_exec_frames(const uint64_t *work, const uint8_t *eligible, size_t nframes, uint32_t sms, std::vector<uint32_t> &cta_frames);
+// The order in which k_fse takes the blocks (PipelineArgs::fse_order): row by row (block-in-frame index) across the frames that are
+// not on k_exec_cta, inside a row by decreasing sequence count, then the blocks of k_exec_cta's frames, frame after frame.  Left
+// empty (= descriptor order) when no frame of the warp kernel has two blocks or the frames do not cover the blocks exactly.
+void build_fse_order(const uint32_t *first_block, const uint32_t *nblocks, const uint8_t *on_cta, size_t nframes, const uint32_t *nseq,
+                     size_t nblocks_total, std::vector<uint32_t> &order);
+
 inline uint32_t host_status(uint32_t code, uint32_t stage, uint32_t pos) { return code | (stage << 16) | (pos << 24); }
 
 // XXH64 (seed 0) streaming -- the hash the reference feeds on drain (decode_buffer.rs:42,225,290,301)
